@@ -1,0 +1,52 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_case(name):
+    """Golden fixture -> (cov_mats, reads, kwargs, outputs dict).  Fixtures come from the real reference
+    (oracle/gen_golden.py)."""
+    d = np.load(os.path.join(GOLDEN, name + ".npz"))
+    p = int(d["p"])
+    mats = []
+    pos = 0
+    for L, f in zip(d["lengths"], d["layout_f"]):
+        L = int(L)
+        m = d["cov_flat"][pos:pos + p * L].reshape(p, L).copy()
+        if f:
+            m = np.asfortranarray(m)
+        mats.append(m)
+        pos += p * L
+    kwargs = {}
+    for k, v in zip(d["kw_keys"], d["kw_vals"]):
+        k = str(k)
+        kwargs[k] = bool(v) if k == "skip_baseline_selection" else int(v)
+    ests = []
+    pos = 0
+    for L in d["lengths"]:
+        L = int(L)
+        ests.append(d["est_flat"][pos:pos + p * L].reshape(p, L))
+        pos += p * L
+    out = {k: d[k] for k in ("rho", "x_adj", "scale_factors", "norm_factors", "x_weighted", "ran", "nmf_widths")}
+    out["estimates"] = ests
+    return mats, d["reads"].copy(), kwargs, out
+
+
+RUN_CASES = ["run_p4", "run_p4_ds", "run_p12", "run_skip", "run_p3_bins"]
+
+
+@pytest.fixture(scope="session")
+def golden_loader():
+    return load_case
