@@ -1,0 +1,5 @@
+"""degnorm_b200: B200-native NMF-OA engine, drop-in for the GeneNMFOA path of NUStatBioinfo/DegNorm."""
+__version__ = "0.1.0"
+
+from .nmf import GeneNMFOA          # noqa: F401
+from .engine import Params, ShardEngine, draw_offsets   # noqa: F401

@@ -1,0 +1,243 @@
+"""
+Device engine of the NMF-OA path: owns one GPU's shard of genes (ragged CSR coverage buffer + read counts)
+and drives the CUDA library (include/degnorm_b200.h) through the whole GeneNMFOA.run flow
+(reference: degnorm/nmf.py:483-601; distributed twin: degnorm/nmf_mpi.py:555-863).
+
+PyTorch is used for device memory, streams and (with several GPUs) the NCCL all-reduce of the per-sample
+sums; every arithmetic step of the path runs in the library's kernels.  No CPU fallback.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DnParams, DnPlan, check
+
+RESIDENT_TIERS = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
+
+
+class Params(object):
+    """Constructor arguments normalised exactly as GeneNMFOA.__init__ does (nmf.py:30-53)."""
+
+    def __init__(self, degnorm_iter=5, downsample_rate=1, min_high_coverage=50, nmf_iter=100, bins=20, n_jobs=1,
+                 skip_baseline_selection=False, random_state=123):
+        self.degnorm_iter = abs(int(degnorm_iter))
+        self.nmf_iter = abs(int(nmf_iter))
+        self.n_jobs = abs(int(n_jobs))
+        self.bins = abs(int(bins))
+        self.min_high_coverage = max(2, abs(int(min_high_coverage)))
+        self.min_bins = int(math.ceil(self.bins * 0.2))
+        self.downsample_rate = abs(int(downsample_rate))
+        self.skip_baseline_selection = bool(skip_baseline_selection)
+        self.random_state = random_state
+        if self.downsample_rate > 1:
+            self.min_high_coverage = 2
+        if self.downsample_rate < 1:
+            raise ValueError("downsample_rate must be >= 1")
+
+    def to_c(self, p):
+        # nmf.py:261 evaluates max(2, ceil(200.0 * (1 / rate))) in floating point; do the same
+        min_len = int(max(2, np.ceil(200.0 * (1 / self.downsample_rate))))
+        return DnParams(int(p), self.nmf_iter, self.bins, self.min_bins, self.min_high_coverage,
+                        self.downsample_rate, min_len, int(self.skip_baseline_selection))
+
+
+def draw_offsets(n_genes, prm):
+    """Systematic-sample start offsets, one per gene per outer iteration, from the GLOBAL legacy numpy stream
+    exactly as the reference consumes it: run() calls np.random.seed(random_state) (nmf.py:556) and every
+    baseline_selection call draws np.random.choice(rate) (nmf.py:420-422), genes in order, iteration-major.
+    The seeding of the global stream is a side effect the reference has; it is kept."""
+    np.random.seed(prm.random_state)
+    if prm.downsample_rate <= 1:
+        return None
+    out = np.empty((prm.degnorm_iter, n_genes), dtype=np.int32)
+    for it in range(prm.degnorm_iter):
+        for g in range(n_genes):
+            out[it, g] = np.random.choice(prm.downsample_rate)
+    return out
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class _Bucket(object):
+    __slots__ = ("plan", "order", "n", "ws", "stream", "max_cols")
+
+
+class ShardEngine(object):
+    """One GPU's shard.  load() takes device tensors; run() leaves device tensors in self.out."""
+
+    def __init__(self, prm, p, device, group=None, force_streamed=False):
+        self.prm = prm
+        self.p = int(p)
+        self.device = torch.device(device)
+        self.group = group
+        self.force_streamed = force_streamed
+        self.cprm = prm.to_c(p)
+        with torch.cuda.device(self.device):
+            self.sm_count, self.max_smem, self.cc = _lib.device_info()
+        self.lib = _lib.lib()
+        self.launches = 0
+
+    # ---------------------------------------------------------------------------------------------------------
+    def load(self, cov, offsets, reads):
+        """cov: 1-D float64 device tensor (ragged CSR buffer); offsets: int64 numpy [n+1]; reads: n x p float64
+        device tensor (this shard's rows)."""
+        assert cov.dtype == torch.float64 and cov.is_cuda and cov.is_contiguous()
+        self.cov = cov
+        self.offsets_np = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.n = len(self.offsets_np) - 1
+        self.lengths = np.diff(self.offsets_np)
+        if self.n and int(self.lengths.max()) >= 2 ** 31 - 1:
+            raise ValueError("gene longer than 2^31-2 positions")
+        self.off_dev = torch.from_numpy(self.offsets_np).to(self.device)
+        self.reads = reads.contiguous()
+        self._plan()
+
+    def _make_plan(self, max_cols, n_work, want_resident, for_init=False):
+        plan = DnPlan()
+        check(self.lib.dn_make_plan(C.byref(self.cprm), int(max_cols), int(n_work), int(want_resident),
+                                    int(for_init), self.sm_count, self.max_smem, C.byref(plan)))
+        return plan
+
+    def _bucket(self, ids, cand, want_resident, for_init=False):
+        b = _Bucket()
+        order = ids[np.argsort(-cand[ids], kind="stable")]
+        b.n = len(order)
+        b.max_cols = int(cand[ids].max())
+        b.plan = self._make_plan(b.max_cols, b.n, want_resident, for_init)
+        b.order = torch.from_numpy(order.astype(np.int32)).to(self.device)
+        b.ws = torch.empty(int(b.plan.ws_bytes), dtype=torch.uint8, device=self.device)
+        b.stream = torch.cuda.Stream(device=self.device)
+        return b
+
+    def _plan(self):
+        n, L, r = self.n, self.lengths, self.prm.downsample_rate
+        self.buckets = []
+        self.init_bucket = None
+        if n == 0:
+            return
+        # init pass (ratio_svd): every gene, all columns, coverage read in place
+        self.init_bucket = self._bucket(np.arange(n), L, 0, for_init=True)
+        # baseline selection: bucket by the number of candidate columns, ceil(L / rate)
+        cand = (L + r - 1) // r
+        if self.force_streamed:
+            self.buckets.append(self._bucket(np.arange(n), cand, 0))
+            return
+        left = np.ones(n, dtype=bool)
+        prev = 0
+        for tier in RESIDENT_TIERS:
+            plan = self._make_plan(tier, 1, tier)
+            if plan.resident_cols < tier:
+                break
+            sel = np.flatnonzero(left & (cand <= tier) & (cand > prev))
+            if len(sel):
+                self.buckets.append(self._bucket(sel, cand, tier))
+                left[sel] = False
+            prev = tier
+        rest = np.flatnonzero(left)
+        if len(rest):
+            self.buckets.append(self._bucket(rest, cand, -1))
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _allreduce(self, t):
+        if self.group is not None:
+            torch.distributed.all_reduce(t, group=self.group)
+
+    def run(self, ds_offsets=None, want_estimates=True):
+        """ds_offsets: int32 numpy [degnorm_iter, n] (this shard's genes) or None.  Results -> self.out."""
+        prm, p, n, dev, lib = self.prm, self.p, self.n, self.device, self.lib
+        f64 = dict(dtype=torch.float64, device=dev)
+        main = torch.cuda.current_stream(dev)
+        n_iter = prm.degnorm_iter
+        nn = max(n, 1)
+        est_rs = torch.zeros((nn, p), **f64)
+        cov_rs = torch.zeros((nn, p), **f64)
+        rho = torch.zeros((nn, p), **f64)
+        rho0 = torch.zeros((nn, p), **f64)
+        x_w = torch.zeros((nn, p), **f64)
+        x_adj = torch.zeros((nn, p), **f64)
+        norm = torch.zeros(p, **f64)
+        scale = torch.zeros(p, **f64)
+        sums = torch.zeros(3 * p + 1, **f64)
+        ran = torch.zeros((max(n_iter, 1), nn), dtype=torch.uint8, device=dev)
+        counters = torch.zeros((max(n_iter, 1), nn, _lib.DN_NCOUNTERS), dtype=torch.int32, device=dev)
+        init_counters = torch.zeros((nn, _lib.DN_NCOUNTERS), dtype=torch.int32, device=dev)
+        sums_ws = torch.empty(int(lib.dn_sums_workspace_bytes(nn, p)), dtype=torch.uint8, device=dev)
+        kfac = torch.zeros((nn, p), **f64)
+        want_e_first = want_estimates and prm.downsample_rate == 1 and n > 0
+        e_first = torch.zeros(int(self.offsets_np[-1]), **f64) if want_e_first else None
+        ds_dev = torch.from_numpy(np.ascontiguousarray(ds_offsets, dtype=np.int32)).to(dev) if ds_offsets is not None else None
+        self.launches = 0
+
+        # ---- init: ratio_svd row sums -> rho0, low-DI genes, norm factors (nmf.py:521-535)
+        if n > 0:
+            b = self.init_bucket
+            check(lib.dn_init_ratio_svd(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm),
+                                        C.byref(b.plan), _ptr(est_rs), _ptr(cov_rs), _ptr(init_counters), _ptr(b.ws),
+                                        b.ws.numel(), C.c_void_p(main.cuda_stream)))
+            check(lib.dn_init_sums(_ptr(est_rs), _ptr(cov_rs), _ptr(self.reads), n, p, _ptr(rho0), _ptr(sums),
+                                   _ptr(sums_ws), sums_ws.numel(), C.c_void_p(main.cuda_stream)))
+            self.launches += 3
+        self._allreduce(sums)
+        check(lib.dn_init_apply(_ptr(sums), _ptr(self.reads), nn if n == 0 else n, p, _ptr(x_w), _ptr(norm), _ptr(scale),
+                                C.c_void_p(main.cuda_stream)))
+        self.launches += 1
+        scale_used = scale.clone()
+
+        # ---- outer DegNorm iterations (nmf.py:560-596)
+        for it in range(n_iter):
+            last = it == n_iter - 1
+            scale_used.copy_(scale)
+            for b in self.buckets:
+                b.stream.wait_stream(main)
+                check(lib.dn_baseline_selection(
+                    _ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm), C.byref(b.plan),
+                    _ptr(scale), _ptr(ds_dev[it]) if ds_dev is not None else C.c_void_p(0),
+                    _ptr(rho), _ptr(ran[it]), _ptr(counters[it]), _ptr(kfac),
+                    _ptr(e_first) if (last and e_first is not None) else C.c_void_p(0),
+                    _ptr(b.ws), b.ws.numel(), C.c_void_p(b.stream.cuda_stream)))
+                self.launches += 1
+            for b in self.buckets:
+                main.wait_stream(b.stream)
+            if n > 0:
+                check(lib.dn_outer_sums(_ptr(x_w), _ptr(rho), n, p, _ptr(sums), _ptr(sums_ws), sums_ws.numel(),
+                                        C.c_void_p(main.cuda_stream)))
+                self.launches += 2
+            else:
+                sums.zero_()
+            self._allreduce(sums)
+            check(lib.dn_outer_apply(_ptr(sums), nn if n == 0 else n, p, _ptr(x_w), _ptr(rho), _ptr(x_adj), _ptr(norm),
+                                     _ptr(scale), C.c_void_p(main.cuda_stream)))
+            self.launches += 1
+
+        est = None
+        if want_estimates and n > 0 and n_iter > 0:
+            est = torch.empty_like(self.cov)
+            b = self.init_bucket
+            check(lib.dn_estimates(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm),
+                                   _ptr(scale_used), _ptr(counters[n_iter - 1]), _ptr(kfac), _ptr(e_first), _ptr(est),
+                                   C.c_void_p(main.cuda_stream)))
+            self.launches += 1
+        self.out = dict(rho=rho[:n], rho0=rho0[:n], x_adj=x_adj[:n], x_weighted=x_w[:n], norm_factors=norm,
+                        scale_factors=scale, ran=ran[:, :n], counters=counters[:, :n], init_counters=init_counters[:n],
+                        est=est, kfac=kfac[:n], scale_used=scale_used)
+        return self.out
+
+    # ---------------------------------------------------------------------------------------------------------
+    def algorithmic_bytes(self):
+        """bytes the path would move if every pass were streamed from HBM,
+        from the per-gene device counters.  Returns (total, per-part dict)."""
+        prm, p = self.prm, self.p
+        T = prm.nmf_iter
+        Lsum = float(self.lengths.sum())
+        cnt = self.out["counters"].to(torch.int64)
+        sum_cols = float(cnt[:, :, _lib.CNT_SUM_COLS].sum().item())
+        init = 16.0 * p * Lsum
+        scan = 8.0 * p * Lsum * prm.degnorm_iter
+        nmf = (24.0 * T + 24.0) * p * sum_cols
+        est = 8.0 * p * Lsum if self.out["est"] is not None else 0.0
+        return init + scan + nmf + est, dict(init=init, scan=scan, nmf=nmf, est=est, sum_cols=sum_cols)

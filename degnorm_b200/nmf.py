@@ -1,0 +1,203 @@
+"""
+Drop-in for the reference's degnorm/nmf.py: class GeneNMFOA with the same constructor, run(), save_results()
+and public attributes (nmf.py:10-711), backed by the B200 CUDA engine.  The CLI callers
+(degnorm/__main__.py:264-286) work unchanged against this class.
+
+Differences from the reference that are deliberate and documented in DESIGN.md:
+  * n_jobs is accepted and ignored (the GPU owns the gene-level parallelism; joblib threads are gone).
+  * the rank-one step is a p x p Gram eigen-solve instead of scipy svds; K >= 0 by convention.
+  * extras that do not exist in the reference: `device=`, `return_estimates=` keyword arguments and the
+    `counters` / `timings` attributes.
+"""
+import logging
+import os
+import pickle as pkl
+import time
+import warnings
+
+import numpy as np
+import torch
+
+from .engine import Params, ShardEngine, draw_offsets
+from .packing import pack_coverage, unpack_estimates
+
+
+class GeneNMFOA(object):
+
+    def __init__(self, degnorm_iter=5, downsample_rate=1, min_high_coverage=50, nmf_iter=100, bins=20, n_jobs=1,
+                 skip_baseline_selection=False, random_state=123, device=None, return_estimates=True):
+        prm = Params(degnorm_iter=degnorm_iter, downsample_rate=downsample_rate,
+                     min_high_coverage=min_high_coverage, nmf_iter=nmf_iter, bins=bins, n_jobs=n_jobs,
+                     skip_baseline_selection=skip_baseline_selection, random_state=random_state)
+        self._prm = prm
+        # same attribute names as the reference (nmf.py:30-49)
+        self.degnorm_iter = prm.degnorm_iter
+        self.nmf_iter = prm.nmf_iter
+        self.n_jobs = prm.n_jobs
+        self.bins = prm.bins
+        self.min_high_coverage = prm.min_high_coverage
+        self.min_bins = prm.min_bins
+        self.downsample_rate = prm.downsample_rate
+        self.mem_splits = None
+        self.x = None
+        self.x_weighted = None
+        self.x_adj = None
+        self.p = None
+        self.n_genes = None
+        self.genes = None
+        self.norm_factors = None
+        self.scale_factors = None
+        self.rho = None
+        self.fitted = False
+        self.ran_baseline_selection = None
+        self.skip_baseline_selection = skip_baseline_selection
+        self.random_state = random_state
+        self.device = device
+        self.return_estimates = return_estimates
+        self.counters = None
+        self.timings = {}
+
+    # ---- small host helpers the reference exposes as (static) methods -------------------------------------------
+    @staticmethod
+    def get_high_coverage_idx(x):
+        """nmf.py:66-76"""
+        return np.where(x.max(axis=0) > 0.1 * x.max())[0]
+
+    @staticmethod
+    def shift_bins(bins, dropped_bin):
+        """nmf.py:160-187: re-index bins after `dropped_bin` has been deleted so they stay consecutive."""
+        if dropped_bin == len(bins) or len(bins) == 1:
+            return bins
+        delta = bins[0][0] if dropped_bin == 0 else bins[dropped_bin][0] - bins[dropped_bin - 1][-1] - 1
+        for k in range(dropped_bin, len(bins)):
+            bins[k] = [idx - delta for idx in bins[k]]
+        return bins
+
+    @staticmethod
+    def _systematic_sample(n, take_every):
+        """nmf.py:408-426 (draws from the global legacy numpy stream, like the reference)."""
+        if take_every >= n:
+            return int(np.random.choice(n))
+        start = np.random.choice(take_every)
+        return np.arange(start, n, step=take_every, dtype=int)
+
+    def downsample_2d(self, x, by_row=True):
+        """nmf.py:428-453"""
+        Li = x.shape[0 if by_row else 1]
+        if self.downsample_rate == 1:
+            return x, np.arange(0, Li)
+        if self.downsample_rate >= Li:
+            raise ValueError('Cannot downsample at a rate < 1 / length(gene)')
+        idx = self._systematic_sample(Li, take_every=self.downsample_rate)
+        return (x[idx, :], idx) if by_row else (x[:, idx], idx)
+
+    def check_input(self, cov_mats):
+        """nmf.py:455-481 (same checks, same messages)."""
+        if self.x.shape[0] != self.n_genes:
+            raise ValueError('Number of genes in read count matrix not equal to number of coverage matrices!')
+        if not all(map(lambda z: z.ndim == 2, cov_mats)):
+            raise ValueError('Not all coverage matrices are 2-d arrays!')
+        li_vec = np.array([m.shape[1] for m in cov_mats])
+        if np.sum(li_vec / self.p < 1) > 0:
+            logging.warning('At least one coverage matrix is taller than it is wide.'
+                            'Ensure that coverage matrices are shaped (p x L_i).')
+        if self.downsample_rate > 1:
+            if not np.min(li_vec) >= self.downsample_rate:
+                raise ValueError('downsample_rate is too large; take-every size > at least one gene.')
+        if not all(m.shape[0] == self.p for m in cov_mats):
+            raise ValueError('Not all coverage matrices have the same number of samples (rows)!')
+
+    # ---- the hot path ---------------------------------------------------------------------------------------------
+    def run(self, cov_dat, reads_dat):
+        """GeneNMFOA.run (nmf.py:483-601): returns the list of estimated coverage matrices (p x L_g, cov_dat key
+        order) of the last outer iteration and sets rho, x_adj, scale_factors, norm_factors, x_weighted,
+        ran_baseline_selection, genes, p, n_genes, fitted."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("degnorm_b200 needs a CUDA device (B200); there is no CPU fallback")
+        t0 = time.perf_counter()
+        self.n_genes = len(cov_dat)
+        self.genes = list(cov_dat.keys())
+        self.x = np.copy(reads_dat)
+        cov_mats = list(cov_dat.values())
+        self.p = cov_mats[0].shape[0]
+        self.ran_baseline_selection = np.zeros(shape=[self.n_genes, self.degnorm_iter]).astype(bool)
+        self.check_input(cov_mats)
+        mem_splits = int(np.ceil(np.sum([m.nbytes for m in cov_mats]) / 5e7))
+        self.mem_splits = max(mem_splits, self.n_jobs)
+
+        dev = torch.device(self.device if self.device is not None else "cuda:%d" % torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            flat, offsets = pack_coverage(cov_mats, self.p)                     # pinned host staging
+            t1 = time.perf_counter()
+            cov_dev = flat.to(dev, non_blocking=True)
+            reads_dev = torch.from_numpy(np.ascontiguousarray(self.x, dtype=np.float64)).to(dev)
+            eng = ShardEngine(self._prm, self.p, dev)
+            eng.load(cov_dev, offsets, reads_dev)
+            ds = draw_offsets(self.n_genes, self._prm)        # also seeds the global numpy stream (nmf.py:556)
+            out = eng.run(ds, want_estimates=self.return_estimates)
+            torch.cuda.synchronize(dev)
+            t2 = time.perf_counter()
+            self.rho = out["rho"].cpu().numpy()
+            self.x_adj = out["x_adj"].cpu().numpy()
+            self.x_weighted = out["x_weighted"].cpu().numpy()
+            self.norm_factors = out["norm_factors"].cpu().numpy()
+            self.scale_factors = out["scale_factors"].cpu().numpy()
+            self.ran_baseline_selection = out["ran"].cpu().numpy().T.astype(bool)
+            self.counters = out["counters"].cpu().numpy()
+            estimates = None
+            if self.return_estimates and out["est"] is not None:
+                estimates = unpack_estimates(out["est"], offsets, self.p)
+            t3 = time.perf_counter()
+        self._engine = eng
+        self.fitted = True
+        self.timings = dict(pack_s=t1 - t0, device_s=t2 - t1, unpack_s=t3 - t2, total_s=t3 - t0,
+                            launches=eng.launches)
+        return estimates
+
+    # ---- output writer (host side, same files and columns as nmf.py:603-711) --------------------------------------
+    def save_results(self, estimates, gene_manifest_df, output_dir='.', sample_ids=None):
+        from pandas import DataFrame, concat
+        if not self.fitted:
+            raise ValueError('Model not yet fit. NMF-OA has not been run.')
+        if not os.path.isdir(output_dir):
+            raise IOError('Directory {0} not found.'.format(output_dir))
+        if not all([col in gene_manifest_df.columns.tolist() for col in ['chr', 'gene']]):
+            raise ValueError('gene_manifest_df must have columns `chr` and `gene`.')
+        if sample_ids:
+            if len(sample_ids) != self.p:
+                raise ValueError('Number of supplied sample IDs does not match number'
+                                 'of samples used to fit GeneNMFOA object.')
+        else:
+            sample_ids = ['sample_{0}'.format(i + 1) for i in range(self.p)]
+        gene_intersect = np.intersect1d(gene_manifest_df.gene.unique(), self.genes)
+        if len(gene_intersect) < len(self.genes):
+            warnings.warn('Gene manifest data does not encompass set of genes sent through DegNorm.')
+        if len(gene_intersect) == 0:
+            raise ValueError('No genes used in DegNorm were found in gene manifest dataframe!')
+        gene_df = gene_manifest_df[gene_manifest_df.gene.isin(gene_intersect)]
+        manifest_chroms = gene_df.chr.unique().tolist()
+        first_chrom = gene_df.drop_duplicates('gene').set_index('gene').chr
+        position = {g: i for i, g in reversed(list(enumerate(self.genes)))}
+        chrom_gene_dict = {chrom: dict() for chrom in manifest_chroms}
+        for gene in gene_intersect:
+            chrom_gene_dict[first_chrom[gene]][gene] = estimates[position[gene]]
+        chrom_gene_dfs = list()
+        for chrom in manifest_chroms:
+            chrom_dir = os.path.join(output_dir, str(chrom))
+            if not os.path.isdir(chrom_dir):
+                os.makedirs(chrom_dir)
+            with open(os.path.join(chrom_dir, 'estimated_coverage_matrices_{0}.pkl'.format(chrom)), 'wb') as f:
+                pkl.dump(chrom_gene_dict[chrom], f)
+            chrom_gene_dfs.append(DataFrame({'chr': chrom, 'gene': list(chrom_gene_dict[chrom].keys())}))
+        chrom_gene_df = concat(chrom_gene_dfs)
+        chrom_gene_df.set_index('gene', inplace=True)
+        chrom_gene_df = chrom_gene_df.loc[self.genes]
+        chrom_gene_df.reset_index(inplace=True)
+        chrom_gene_df = chrom_gene_df[['chr', 'gene']]
+        iter_names = ['iter_{0}'.format(i) for i in range(self.degnorm_iter)]
+        for mat, cols, fname in ((self.rho, sample_ids, 'degradation_index_scores.csv'),
+                                 (self.x_adj, sample_ids, 'adjusted_read_counts.csv'),
+                                 (self.ran_baseline_selection, iter_names, 'ran_baseline_selection.csv')):
+            df = concat([chrom_gene_df, DataFrame(mat, columns=cols)], axis=1)
+            df = df[['chr', 'gene'] + cols]
+            df.to_csv(os.path.join(output_dir, fname), index=False)

@@ -40,11 +40,15 @@ def gene_lengths(n_genes, rng, profile="pc", lmin=None, lmax=None):
     return np.clip(L, lo, hi)
 
 
-def synth_numpy(n_genes, p, seed, profile="pc", lmin=None, lmax=None, fortran_every=0, lengths=None):
+def synth_numpy(n_genes, p, seed, profile="pc", lmin=None, lmax=None, fortran_every=0, lengths=None, jitter=0.0):
     """
     Returns (cov_mats, reads): list of n_genes float64 p x L_g arrays and an n_genes x p float64 count
     matrix.  fortran_every=k makes every k-th gene Fortran-contiguous (the reference's merge step emits
     both layouts -- reads_coverage_merge.py:331,353 vs :155-159).
+    jitter > 0 multiplies every count by (1 + jitter*u), u ~ U(0,1): integer counts make the reference's
+    high-coverage test `max_i F_ij > 0.1*max(F)` (nmf.py:76) an EXACT tie whenever a column maximum is one tenth
+    of the matrix maximum, and the outcome then hangs on the last bit of the scale factors; parity fixtures use
+    jittered counts so that the reference's answer is well defined ("ties").
     """
     rng = np.random.default_rng(seed)
     if lengths is None:
@@ -76,6 +80,8 @@ def synth_numpy(n_genes, p, seed, profile="pc", lmin=None, lmax=None, fortran_ev
         ramp = 1.0 - slope[:, None] * (1.0 - j[None, :] / L)
         F = rng.poisson(abundance[:, None] * env[None, :] * ramp).astype(np.float64)
         reads[g] = np.rint(F.sum(axis=1) / 100.0)
+        if jitter > 0.0:
+            F = F * (1.0 + jitter * rng.random(F.shape))
         if fortran_every and g % fortran_every == fortran_every - 1:
             F = np.asfortranarray(F)
         cov_mats.append(F)

@@ -38,6 +38,7 @@ import degnorm.nmf as ref_nmf                      # noqa: E402  (the real refer
 from degnorm_b200.synth import synth_numpy         # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
+J = 1.0e-6          # tie-breaking jitter of the synthetic counts (synth_numpy docstring)
 logging.getLogger().setLevel(logging.ERROR)
 
 
@@ -128,19 +129,23 @@ def main(which):
     cases = {
         "kat": case_kat,
         "run_p4": lambda: save_case(
-            "run_p4", *synth_numpy(10, 4, 101, lengths=lengths_uniform(10, 150, 1300, 1), fortran_every=3),
+            "run_p4", *synth_numpy(10, 4, 101, lengths=lengths_uniform(10, 150, 1300, 1), fortran_every=3, jitter=J),
             dict(degnorm_iter=3, nmf_iter=100)),
         "run_p4_ds": lambda: save_case(
-            "run_p4_ds", *synth_numpy(8, 4, 102, lengths=lengths_uniform(8, 600, 4000, 2)),
+            "run_p4_ds", *synth_numpy(8, 4, 102, lengths=lengths_uniform(8, 600, 4000, 2), jitter=J),
+            dict(degnorm_iter=3, nmf_iter=100, downsample_rate=5), private_svds_rng=True),
+        # integer counts: exact ties in the high-coverage test (see synth_numpy's docstring)
+        "run_p4_ds_ties": lambda: save_case(
+            "run_p4_ds_ties", *synth_numpy(8, 4, 102, lengths=lengths_uniform(8, 600, 4000, 2)),
             dict(degnorm_iter=3, nmf_iter=100, downsample_rate=5), private_svds_rng=True),
         "run_p12": lambda: save_case(
-            "run_p12", *synth_numpy(6, 12, 103, lengths=lengths_uniform(6, 250, 1000, 3)),
+            "run_p12", *synth_numpy(6, 12, 103, lengths=lengths_uniform(6, 250, 1000, 3), jitter=J),
             dict(degnorm_iter=2, nmf_iter=100)),
         "run_skip": lambda: save_case(
-            "run_skip", *synth_numpy(8, 4, 104, lengths=lengths_uniform(8, 150, 1500, 4)),
+            "run_skip", *synth_numpy(8, 4, 104, lengths=lengths_uniform(8, 150, 1500, 4), jitter=J),
             dict(degnorm_iter=2, nmf_iter=60, skip_baseline_selection=True)),
         "run_p3_bins": lambda: save_case(
-            "run_p3_bins", *synth_numpy(6, 3, 105, lengths=lengths_uniform(6, 220, 900, 5)),
+            "run_p3_bins", *synth_numpy(6, 3, 105, lengths=lengths_uniform(6, 220, 900, 5), jitter=J),
             dict(degnorm_iter=2, nmf_iter=40, bins=10, min_high_coverage=30)),
     }
     for name in (which or list(cases)):

@@ -45,6 +45,7 @@ def load_case(name):
 
 
 RUN_CASES = ["run_p4", "run_p4_ds", "run_p12", "run_skip", "run_p3_bins"]
+TIE_CASE = "run_p4_ds_ties"      # integer counts: exact ties in the high-coverage test (DESIGN.md "ties")
 
 
 @pytest.fixture(scope="session")
