@@ -46,7 +46,10 @@ int fail(int code, const char *fmt, const char *a = "", long long b = 0, long lo
     } while (0)
 
 constexpr double EIG_TOL = 1.0e-14;
-constexpr int EIG_MAX_STEPS = 20000;
+constexpr int EIG_FAST_STEPS = 64;     // power steps on G before the squaring fallback takes over
+constexpr int EIG_MAX_SQUARINGS = 64;
+constexpr double EIG_SUSPECT = 1.0e-3;  // eigenvector entry below this fraction of the largest, on a covered sample:
+                                        // distrust the warm start (its overlap with a new top eigenvector may be lost)
 constexpr int N_SMALL = 10;        // PP-sized shared vectors
 constexpr int MODE_INIT = 0;       // ratio_svd on raw coverage (nmf.py:109-121)
 constexpr int MODE_BS = 1;         // baseline_selection (nmf.py:189-372)
@@ -163,6 +166,8 @@ struct Gene {
     int nb0;         // bins at the start
     int nalive;
     int eig_steps;
+    int eig_fallbacks;
+    double *B0;      // 2 * pp * pp doubles of global scratch for the small-gap eigen fallback
 };
 
 __device__ __forceinline__ int phys_col(const Gene &g, int vc) {
@@ -173,7 +178,7 @@ __device__ __forceinline__ int phys_col(const Gene &g, int vc) {
 
 // ---- top eigenvector of G (p x p, symmetric, non-negative) by power iteration ---------------------------------
 // Warp version: G in shared memory, p <= 64 (two rows per lane).  Called by warp 0 only.
-__device__ int eig_warp(const double *G, int pp, int p, double *v, bool cold) {
+__device__ int eig_warp(const double *G, int pp, int p, double *v, bool cold, int *conv) {
     const int lane = threadIdx.x & 31;
     const int r0 = lane, r1 = lane + 32;
     double v0 = 0.0, v1 = 0.0;
@@ -197,8 +202,9 @@ __device__ int eig_warp(const double *G, int pp, int p, double *v, bool cold) {
         if (r1 < pp) v1 = v[r1];
     }
     int steps = 0;
+    int ok = 0;
     double prev = 1.0e300;
-    for (; steps < EIG_MAX_STEPS;) {
+    for (; steps < EIG_FAST_STEPS;) {
         double y0 = 0.0, y1 = 0.0;
         if (p <= 32) {
             if (r0 < p) {
@@ -219,6 +225,7 @@ __device__ int eig_warp(const double *G, int pp, int p, double *v, bool cold) {
             if (r0 < pp) v[r0] = 0.0;
             if (r1 < pp) v[r1] = 0.0;
             __syncwarp();
+            ok = 1;
             break;
         }
         double inv = 1.0 / sqrt(n2);
@@ -230,16 +237,28 @@ __device__ int eig_warp(const double *G, int pp, int p, double *v, bool cold) {
         if (r0 < pp) v[r0] = v0;
         if (r1 < pp) v[r1] = v1;
         __syncwarp();
-        if (d <= EIG_TOL) break;
-        if (d < 1.0e-12 && d >= prev) break;      // stagnated at rounding level
+        if (d <= EIG_TOL) { ok = 1; break; }
+        if (steps >= 8 && d > 0.75 * prev) break;     // small spectral gap: let the squaring solver finish
         prev = d;
     }
+    if (ok == 1) {
+        // A warm start that has lost (underflowed) its component along the true top eigenvector can never regain
+        // it: after an eigenvalue crossing between weakly coupled sample blocks power iteration would "converge"
+        // to the wrong vector.  Entries ~0 on samples that do have coverage are the signature: re-solve robustly.
+        const double m0 = (r0 < p && G[r0 * pp + r0] > 0.0) ? v0 : 1.0;
+        const double m1 = (r1 < p && G[r1 * pp + r1] > 0.0) ? v1 : 1.0;
+        const double vmin = -warp_max(-fmin(m0, m1));
+        const double vmax = warp_max(fmax(v0, v1));
+        if (vmin < EIG_SUSPECT * vmax) ok = 2;
+    }
+    if (lane == 0) *conv = ok;
     return steps;
 }
 
 // Block version: any p <= NT, G anywhere (global for p > 64).  Called by all threads.
 template <int NT>
-__device__ int eig_block(const double *G, int pp, int p, double *v, double *red, bool cold) {
+__device__ int eig_block(const double *G, int pp, int p, double *v, double *red, bool cold, int max_steps, double tol,
+                         bool bail, int *conv) {
     const int i = threadIdx.x;
     double vi = 0.0;
     if (cold) {
@@ -255,8 +274,9 @@ __device__ int eig_block(const double *G, int pp, int p, double *v, double *red,
         if (i < pp) vi = v[i];
     }
     int steps = 0;
+    int ok = 0;
     double prev = 1.0e300;
-    for (; steps < EIG_MAX_STEPS;) {
+    for (; steps < max_steps;) {
         double y = 0.0;
         if (i < p)
             for (int k = 0; k < p; ++k) y = fma(G[(long long)k * pp + i], v[k], y);
@@ -265,6 +285,7 @@ __device__ int eig_block(const double *G, int pp, int p, double *v, double *red,
         if (!(n2 > 0.0)) {
             if (i < pp) v[i] = 0.0;
             __syncthreads();
+            ok = 1;
             break;
         }
         double w = y * (1.0 / sqrt(n2));
@@ -272,11 +293,80 @@ __device__ int eig_block(const double *G, int pp, int p, double *v, double *red,
         vi = w;
         if (i < pp) v[i] = vi;
         __syncthreads();
-        if (d <= 4.0 * EIG_TOL) break;
-        if (d < 1.0e-12 && d >= prev) break;
+        if (d <= tol) { ok = 1; break; }
+        if (bail && steps >= 8 && d > 0.75 * prev) break;
         prev = d;
     }
+    if (ok == 1 && bail) {
+        const double m = (i < p && G[(long long)i * pp + i] > 0.0) ? vi : 1.0;
+        const double vmin = -block_max<NT>(-m, red);
+        const double vmax = block_max<NT>(vi, red);
+        if (vmin < EIG_SUSPECT * vmax) ok = 2;
+    }
+    *conv = ok;
     return steps;
+}
+
+// Small-gap fallback (any p): repeated squaring B <- B.B / trace(B.B) starting from B = G / trace(G) squares the
+// eigenvalue ratio each round, one power step with B per round tracks convergence, two steps with G polish.
+// B0/B1 are per-CTA global scratch (pp*pp doubles each).  Called by all threads.  ARPACK (the reference) resolves
+// such gaps exactly because its Krylov space spans all p dimensions; plain power iteration would need ~1/(1-r) steps.
+template <int NT>
+__device__ int eig_squaring(const double *G, int pp, int p, double *v, double *red, double *B0, double *B1, bool restart) {
+    const int tid = threadIdx.x;
+    const int nn = pp * pp;
+    double tr = 0.0;
+    for (int i = tid; i < p; i += NT) tr += G[(long long)i * pp + i];
+    tr = block_sum<NT>(tr, red);
+    if (!(tr > 0.0)) return 0;
+    const double itr = 1.0 / tr;
+    for (int e = tid; e < nn; e += NT) B0[e] = G[e] * itr;
+    // Always restart from the uniform vector over the samples that have coverage: it has a positive overlap with
+    // the (non-negative) top eigenvector, whereas a warm start may have lost it (see eig_warp).
+    (void)restart;
+    {
+        double one = (tid < p && G[(long long)tid * pp + tid] > 0.0) ? 1.0 : 0.0;
+        const double cntp = block_sum<NT>(one, red);
+        if (tid < pp) v[tid] = cntp > 0.0 ? one / sqrt(cntp) : 0.0;
+    }
+    __syncthreads();
+    double *B = B0, *Bn = B1;
+    int rounds = 0;
+    for (; rounds < EIG_MAX_SQUARINGS;) {
+        double t = 0.0;
+        for (int e = tid; e < nn; e += NT) {
+            const int i = e / pp, j = e - i * pp;
+            double s = 0.0;
+            if (i < p && j < p)
+                for (int k = 0; k < p; ++k) s = fma(B[i * pp + k], B[k * pp + j], s);
+            Bn[e] = s;
+            if (i == j) t += s;
+        }
+        t = block_sum<NT>(t, red);                 // also orders the Bn writes before the reads below
+        ++rounds;
+        if (!(t > 0.0)) break;
+        const double it = 1.0 / t;
+        for (int e = tid; e < nn; e += NT) Bn[e] *= it;
+        __syncthreads();
+        double *sw = B; B = Bn; Bn = sw;
+        // one power step with the squared matrix
+        double y = 0.0, vi = 0.0;
+        if (tid < p) {
+            vi = v[tid];
+            for (int k = 0; k < p; ++k) y = fma(B[k * pp + tid], v[k], y);
+        }
+        const double n2 = block_sum<NT>(y * y, red);
+        if (!(n2 > 0.0)) break;
+        const double w = y * (1.0 / sqrt(n2));
+        const double d = block_max<NT>(tid < p ? fabs(w - vi) : 0.0, red);
+        if (tid < p) v[tid] = w;
+        __syncthreads();
+        // trace(B.B) with trace(B) = 1 reaches 1 exactly when B is numerically rank one
+        if (1.0 - t <= 1.0e-15 && d <= EIG_TOL) break;
+    }
+    int conv;
+    rounds += eig_block<NT>(G, pp, p, v, red, false, 2, 0.0, false, &conv);      // polish with G itself
+    return rounds;
 }
 
 // ---- one pass over the current columns: (optional multiplier update) + Gram accumulate -------------------------
@@ -380,15 +470,22 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
 
 template <int NT>
 __device__ __forceinline__ void eig_solve(const KArgs &a, Gene &g, bool cold) {
+    int conv = 1;
     if (a.g_in_smem) {
         if (threadIdx.x < 32) {
-            int s = eig_warp(g.G, a.pp, a.p, g.v, cold);
+            int s = eig_warp(g.G, a.pp, a.p, g.v, cold, g.ibuf + 12);
             g.eig_steps += s;
         }
         __syncthreads();
+        conv = g.ibuf[12];
     } else {
-        int s = eig_block<NT>(g.G, a.pp, a.p, g.v, g.red, cold);
+        int s = eig_block<NT>(g.G, a.pp, a.p, g.v, g.red, cold, EIG_FAST_STEPS, 4.0 * EIG_TOL, true, &conv);
         g.eig_steps += s;
+    }
+    if (conv != 1) {                               // uniform across the CTA
+        int s = eig_squaring<NT>(g.G, a.pp, a.p, g.v, g.red, g.B0, g.B0 + (long long)a.pp * a.pp, conv == 2);
+        g.eig_steps += s;
+        g.eig_fallbacks += 1;
     }
 }
 
@@ -545,14 +642,16 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
     g.ibuf = reinterpret_cast<int *>(smem + cv.ibuf);
     g.ms = smem + cv.ms;
     double *slab = a.ws + (long long)blockIdx.x * a.ws_stride;
-    long long slab_o = 0;
+    g.B0 = slab;
+    long long slab_o = 2ll * pp * pp;
     if (a.g_in_smem) {
         g.G = smem + cv.G;
     } else {
-        g.G = slab;
-        slab_o = (long long)pp * pp;
+        g.G = slab + slab_o;
+        slab_o += (long long)pp * pp;
     }
     g.eig_steps = 0;
+    g.eig_fallbacks = 0;
 
     // Gram tile owned by this thread
     const int ntg = pp / TR;
@@ -582,6 +681,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
         const double *F = a.cov + (long long)p * o0;
         int *cnt = a.counters ? a.counters + (long long)gid * DN_NCOUNTERS : nullptr;
         g.eig_steps = 0;
+        g.eig_fallbacks = 0;
 
         if (a.mode == MODE_INIT) {
             // ratio_svd on the raw matrix: all columns, no scaling, no multiplier updates
@@ -612,7 +712,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
             if (cnt && tid == 0) {
                 cnt[DN_CNT_EXIT] = 0; cnt[DN_CNT_N_HICOV] = L; cnt[DN_CNT_NMF_CALLS] = 1; cnt[DN_CNT_SUM_COLS] = L;
                 cnt[DN_CNT_EIG_STEPS] = g.eig_steps; cnt[DN_CNT_DROPS_LO] = 0; cnt[DN_CNT_DROPS_HI] = 0;
-                cnt[DN_CNT_RESIDENT] = res_ok;
+                cnt[DN_CNT_RESIDENT] = (int)res_ok | (g.eig_fallbacks << 1);
             }
             __syncthreads();
             continue;
@@ -830,7 +930,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
                 cnt[DN_CNT_EXIT] = exit_code; cnt[DN_CNT_N_HICOV] = n0; cnt[DN_CNT_NMF_CALLS] = nmf_calls;
                 cnt[DN_CNT_SUM_COLS] = sum_cols; cnt[DN_CNT_EIG_STEPS] = g.eig_steps;
                 cnt[DN_CNT_DROPS_LO] = (int)(drops & 0xffffffffull); cnt[DN_CNT_DROPS_HI] = (int)(drops >> 32);
-                cnt[DN_CNT_RESIDENT] = resident;
+                cnt[DN_CNT_RESIDENT] = (int)resident | (g.eig_fallbacks << 1);
             }
         }
         __syncthreads();
@@ -1095,7 +1195,7 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     a.queue = (int *)workspace;
     a.ws = (double *)((char *)workspace + 256);
     a.ws_ld = plan->ws_cols;
-    const long long g_d = d.g_in_smem ? 0 : (long long)d.pp * d.pp;
+    const long long g_d = (d.g_in_smem ? 2ll : 3ll) * d.pp * d.pp;
     const long long cols_d = mode == MODE_INIT ? plan->ws_cols : (2ll * prm->p + 2) * plan->ws_cols;
     a.ws_stride = (g_d + cols_d + 31) / 32 * 32;
     DN_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
@@ -1160,7 +1260,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
     if (ctas > n_work) ctas = n_work;
     if (ctas < 1) ctas = 1;
     plan->ctas = (int32_t)ctas;
-    const long long g_d = d.g_in_smem ? 0 : (long long)d.pp * d.pp;
+    const long long g_d = (d.g_in_smem ? 2ll : 3ll) * d.pp * d.pp;
     const long long cols_d = for_init ? plan->ws_cols : (2ll * prm->p + 2) * plan->ws_cols;
     const long long stride = (g_d + cols_d + 31) / 32 * 32;
     plan->ws_bytes = 256 + ctas * stride * 8;

@@ -62,7 +62,8 @@ typedef enum dn_counter {
     DN_CNT_EIG_STEPS = 4,   /* power-iteration steps spent in the p x p eigen-solves       */
     DN_CNT_DROPS_LO = 5,    /* bit b set: bin b was dropped (bins 0..31)                   */
     DN_CNT_DROPS_HI = 6,    /* bins 32..63                                                 */
-    DN_CNT_RESIDENT = 7     /* 1: gene matrix was held in shared memory, 0: streamed       */
+    DN_CNT_RESIDENT = 7     /* bit 0: gene matrix held in shared memory (else streamed);
+                               bits 1..: eigen-solves that needed the small-gap fallback    */
 } dn_counter;
 
 /* Normalised algorithm parameters: GeneNMFOA.__init__ (nmf.py:12-53) after abs/int/ceil. */

@@ -120,7 +120,7 @@ def test_streamed_tier_equals_resident_tier():
         torch.cuda.synchronize()
         outs.append({k: v.cpu().numpy() for k, v in o.items() if v is not None})
     a, b = outs
-    assert a["counters"][:, :, 7].max() == 1 and b["counters"][:, :, 7].max() == 0
+    assert (a["counters"][:, :, 7] & 1).max() == 1 and (b["counters"][:, :, 7] & 1).max() == 0
     np.testing.assert_array_equal(a["ran"], b["ran"])
     np.testing.assert_array_equal(a["counters"][:, :, :4], b["counters"][:, :, :4])
     np.testing.assert_allclose(a["rho"], b["rho"], rtol=0, atol=1e-12)

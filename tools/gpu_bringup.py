@@ -35,7 +35,8 @@ for case in (sys.argv[1:] or RUN_CASES):
         print("  iter %d: exits %s" % (it, [EXIT_NAMES[int(e)] for e in c[:, 0]]))
         print("          n_hi %s calls gpu %s ref %s  cols gpu %s ref %s  eig_steps/solve %s resident %s" % (
             c[:, 1].tolist(), c[:, 2].tolist(), calls[it].tolist(), c[:, 3].tolist(), cols[it].tolist(),
-            np.round(c[:, 4] / np.maximum(1, c[:, 2] * (m.nmf_iter + 1)), 1).tolist(), c[:, 7].tolist()))
+            np.round(c[:, 4] / np.maximum(1, c[:, 2] * (m.nmf_iter + 1)), 1).tolist(), (c[:, 7] & 1).tolist()))
+        print("          eig fallbacks %s" % (c[:, 7] >> 1).tolist())
     bad = np.argwhere(np.abs(m.rho - ref["rho"]) > 1e-6)
     if len(bad):
         print("  MISMATCH rows:", sorted(set(bad[:, 0].tolist())))
