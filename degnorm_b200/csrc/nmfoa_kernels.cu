@@ -1124,8 +1124,8 @@ int tile_for_p(int p) { return p <= 16 ? 2 : (p <= 64 ? 4 : 8); }
 int check_params(const dn_params *prm) {
     if (!prm) return fail(DN_ERR_INVALID, "null params%s");
     if (prm->p < 2) return fail(DN_ERR_INVALID, "need at least 2 samples%s (p = %lld)", "", prm->p);
-    if (prm->p > DN_MAX_SAMPLES) return fail(DN_ERR_UNSUPPORTED, "p = %lld%s exceeds DN_MAX_SAMPLES", "", prm->p);
-    if (prm->bins < 1 || prm->bins > DN_MAX_BINS) return fail(DN_ERR_UNSUPPORTED, "bins = %lld%s outside [1, DN_MAX_BINS]", "", prm->bins);
+    if (prm->p > DN_MAX_SAMPLES) return fail(DN_ERR_UNSUPPORTED, "%sp = %lld exceeds DN_MAX_SAMPLES", "", prm->p);
+    if (prm->bins < 1 || prm->bins > DN_MAX_BINS) return fail(DN_ERR_UNSUPPORTED, "%sbins = %lld outside [1, DN_MAX_BINS]", "", prm->bins);
     if (prm->downsample_rate < 1) return fail(DN_ERR_INVALID, "downsample_rate must be >= 1%s");
     if (prm->nmf_iter < 0) return fail(DN_ERR_INVALID, "nmf_iter must be >= 0%s");
     return DN_OK;
@@ -1231,7 +1231,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
     if (rc) return rc;
     if (!plan || max_cols < 1 || sm_count < 1 || max_smem_optin < 16 * 1024) return fail(DN_ERR_INVALID, "bad planning argument%s");
     const Derived d = derive(prm->p);
-    if (d.ntiles > d.nt) return fail(DN_ERR_UNSUPPORTED, "p = %lld%s needs more Gram tiles than threads", "", prm->p);
+    if (d.ntiles > d.nt) return fail(DN_ERR_UNSUPPORTED, "%sp = %lld needs more Gram tiles than threads", "", prm->p);
     memset(plan, 0, sizeof(*plan));
     plan->tile = d.tr;
     plan->threads = d.nt;

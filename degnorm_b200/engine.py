@@ -52,11 +52,10 @@ def draw_offsets(n_genes, prm):
     np.random.seed(prm.random_state)
     if prm.downsample_rate <= 1:
         return None
-    out = np.empty((prm.degnorm_iter, n_genes), dtype=np.int32)
-    for it in range(prm.degnorm_iter):
-        for g in range(n_genes):
-            out[it, g] = np.random.choice(prm.downsample_rate)
-    return out
+    # np.random.randint(0, r, size=k) consumes the legacy stream exactly like k successive np.random.choice(r)
+    # calls (tests/test_host_logic.py checks it), so the draws are vectorised
+    out = np.random.randint(0, prm.downsample_rate, size=prm.degnorm_iter * n_genes)
+    return out.reshape(prm.degnorm_iter, n_genes).astype(np.int32)
 
 
 def _ptr(t):
@@ -81,6 +80,8 @@ class ShardEngine(object):
             self.sm_count, self.max_smem, self.cc = _lib.device_info()
         self.lib = _lib.lib()
         self.launches = 0
+        self.record_events = False       # bench.py: CUDA events around each phase, on the launching stream
+        self.events = []
 
     # ---------------------------------------------------------------------------------------------------------
     def load(self, cov, offsets, reads):
@@ -172,6 +173,14 @@ class ShardEngine(object):
         e_first = torch.zeros(int(self.offsets_np[-1]), **f64) if want_e_first else None
         ds_dev = torch.from_numpy(np.ascontiguousarray(ds_offsets, dtype=np.int32)).to(dev) if ds_offsets is not None else None
         self.launches = 0
+        self.events = []
+
+        def mark(name):
+            if self.record_events:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(main)
+                self.events.append((name, e))
+        mark("start")
 
         # ---- init: ratio_svd row sums -> rho0, low-DI genes, norm factors (nmf.py:521-535)
         if n > 0:
@@ -182,6 +191,7 @@ class ShardEngine(object):
             check(lib.dn_init_sums(_ptr(est_rs), _ptr(cov_rs), _ptr(self.reads), n, p, _ptr(rho0), _ptr(sums),
                                    _ptr(sums_ws), sums_ws.numel(), C.c_void_p(main.cuda_stream)))
             self.launches += 3
+        mark("init")
         self._allreduce(sums)
         check(lib.dn_init_apply(_ptr(sums), _ptr(self.reads), nn if n == 0 else n, p, _ptr(x_w), _ptr(norm), _ptr(scale),
                                 C.c_void_p(main.cuda_stream)))
@@ -192,6 +202,7 @@ class ShardEngine(object):
         for it in range(n_iter):
             last = it == n_iter - 1
             scale_used.copy_(scale)
+            mark("pre_bs%d" % it)
             for b in self.buckets:
                 b.stream.wait_stream(main)
                 check(lib.dn_baseline_selection(
@@ -203,6 +214,7 @@ class ShardEngine(object):
                 self.launches += 1
             for b in self.buckets:
                 main.wait_stream(b.stream)
+            mark("bs%d" % it)
             if n > 0:
                 check(lib.dn_outer_sums(_ptr(x_w), _ptr(rho), n, p, _ptr(sums), _ptr(sums_ws), sums_ws.numel(),
                                         C.c_void_p(main.cuda_stream)))
@@ -222,12 +234,28 @@ class ShardEngine(object):
                                    _ptr(scale_used), _ptr(counters[n_iter - 1]), _ptr(kfac), _ptr(e_first), _ptr(est),
                                    C.c_void_p(main.cuda_stream)))
             self.launches += 1
+        mark("end")
         self.out = dict(rho=rho[:n], rho0=rho0[:n], x_adj=x_adj[:n], x_weighted=x_w[:n], norm_factors=norm,
                         scale_factors=scale, ran=ran[:, :n], counters=counters[:, :n], init_counters=init_counters[:n],
                         est=est, kfac=kfac[:n], scale_used=scale_used)
         return self.out
 
     # ---------------------------------------------------------------------------------------------------------
+    def phase_ms(self):
+        """{phase: milliseconds} from the recorded events (call after a synchronize)."""
+        out = {}
+        for (n0, e0), (n1, e1) in zip(self.events[:-1], self.events[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def bs_bytes_per_iteration(self):
+        """Algorithmic bytes of the fused baseline-selection launches of each outer iteration
+        (scan of the raw coverage + every nmf() call as if streamed), SURVEY.md section 8(d)."""
+        prm, p = self.prm, self.p
+        cnt = self.out["counters"].to(torch.int64)
+        sum_cols = cnt[:, :, _lib.CNT_SUM_COLS].sum(dim=1).cpu().numpy().astype(np.float64)
+        return 8.0 * p * float(self.lengths.sum()) + (24.0 * prm.nmf_iter + 24.0) * p * sum_cols
+
     def algorithmic_bytes(self):
         """bytes the path would move if every pass were streamed from HBM,
         from the per-gene device counters.  Returns (total, per-part dict)."""

@@ -8,6 +8,8 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
   * the rank-one step is a p x p Gram eigen-solve instead of scipy svds; K >= 0 by convention.
   * extras that do not exist in the reference: `device=`, `return_estimates=` keyword arguments and the
     `counters` / `timings` attributes.
+  * the estimates returned by run() are views into a pinned host buffer owned by this object; a second run()
+    on the same object re-uses it (copy what must outlive the next run).
 """
 import logging
 import os
@@ -56,6 +58,8 @@ class GeneNMFOA(object):
         self.return_estimates = return_estimates
         self.counters = None
         self.timings = {}
+        self._host_cache = {}      # pinned staging buffers, re-used by later run() calls on this object
+        self._group = None         # torch.distributed group: this object's genes are one shard of a larger run
 
     # ---- small host helpers the reference exposes as (static) methods -------------------------------------------
     @staticmethod
@@ -127,11 +131,11 @@ class GeneNMFOA(object):
 
         dev = torch.device(self.device if self.device is not None else "cuda:%d" % torch.cuda.current_device())
         with torch.cuda.device(dev):
-            flat, offsets = pack_coverage(cov_mats, self.p)                     # pinned host staging
+            flat, offsets = pack_coverage(cov_mats, self.p, cache=self._host_cache)     # pinned host staging
             t1 = time.perf_counter()
             cov_dev = flat.to(dev, non_blocking=True)
             reads_dev = torch.from_numpy(np.ascontiguousarray(self.x, dtype=np.float64)).to(dev)
-            eng = ShardEngine(self._prm, self.p, dev)
+            eng = ShardEngine(self._prm, self.p, dev, group=self._group)
             eng.load(cov_dev, offsets, reads_dev)
             ds = draw_offsets(self.n_genes, self._prm)        # also seeds the global numpy stream (nmf.py:556)
             out = eng.run(ds, want_estimates=self.return_estimates)
@@ -146,7 +150,7 @@ class GeneNMFOA(object):
             self.counters = out["counters"].cpu().numpy()
             estimates = None
             if self.return_estimates and out["est"] is not None:
-                estimates = unpack_estimates(out["est"], offsets, self.p)
+                estimates = unpack_estimates(out["est"], offsets, self.p, cache=self._host_cache)
             t3 = time.perf_counter()
         self._engine = eng
         self.fitted = True

@@ -1,0 +1,113 @@
+"""CPU tests of the host side: parameter normalisation, offsets, packing, the C ABI exports (no GPU calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_params_normalisation_matches_reference_ctor():
+    # nmf.py:30-53
+    from degnorm_b200.engine import Params
+    p = Params(degnorm_iter=-3, downsample_rate=1, min_high_coverage=1, nmf_iter=7.9, bins=12)
+    assert (p.degnorm_iter, p.nmf_iter, p.bins, p.min_high_coverage, p.min_bins) == (3, 7, 12, 2, 3)
+    p = Params(downsample_rate=20, min_high_coverage=50)
+    assert p.min_high_coverage == 2                      # forced when down-sampling (nmf.py:52-53)
+    assert p.to_c(12).min_gene_len == 10                 # max(2, ceil(200 * (1/20)))  nmf.py:261
+    assert Params(downsample_rate=3).to_c(4).min_gene_len == 67
+    assert Params(downsample_rate=500).to_c(4).min_gene_len == 2
+
+
+def test_offsets_follow_the_global_legacy_stream():
+    from degnorm_b200.engine import Params, draw_offsets
+    prm = Params(downsample_rate=20, degnorm_iter=3, random_state=123)
+    off = draw_offsets(7, prm)
+    np.random.seed(123)
+    want = np.array([[np.random.choice(20) for _ in range(7)] for _ in range(3)])
+    np.testing.assert_array_equal(off, want)
+    assert off[0, :6].tolist() == [13, 2, 2, 6, 17, 19]
+    # the reference's visible side effect: the global stream is seeded even without down-sampling (nmf.py:556)
+    np.random.seed(5)
+    assert draw_offsets(3, Params(random_state=99)) is None
+    a = np.random.rand()
+    np.random.seed(99)
+    assert a == np.random.rand()
+
+
+def test_packing_general_and_zero_copy():
+    from degnorm_b200.packing import pack_coverage
+    rng = np.random.default_rng(0)
+    mats = [rng.random((3, L)) for L in (5, 9, 2)]
+    mats[1] = np.asfortranarray(mats[1])
+    flat, off = pack_coverage(mats, 3, pin=False)
+    assert off.tolist() == [0, 5, 14, 16]
+    for g, m in enumerate(mats):
+        np.testing.assert_array_equal(flat.numpy()[3 * off[g]:3 * off[g + 1]].reshape(3, -1), m)
+    # views of one buffer laid out back to back are used in place
+    base = rng.random(3 * 16)
+    views = [base[3 * off[g]:3 * off[g + 1]].reshape(3, -1) for g in range(3)]
+    flat2, off2 = pack_coverage(views, 3, pin=False)
+    assert flat2.numpy().__array_interface__["data"][0] == base.__array_interface__["data"][0]
+    # ... but not when the order or layout differs
+    flat3, _ = pack_coverage([views[1], views[0]], 3, pin=False)
+    assert flat3.numpy().__array_interface__["data"][0] != base.__array_interface__["data"][0]
+    np.testing.assert_array_equal(flat3.numpy()[:27].reshape(3, 9), views[1])
+
+
+def test_library_exports_every_symbol_in_the_header():
+    from degnorm_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "degnorm_b200.h")).read()
+    declared = set(re.findall(r"\b(dn_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"dn_status", "dn_exit", "dn_counter", "dn_params", "dn_plan"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.lib().dn_abi_version() == 1
+
+
+def test_plan_is_pure_host_arithmetic():
+    from degnorm_b200 import _lib
+    from degnorm_b200.engine import Params
+    lib = _lib.lib()
+    prm = Params(downsample_rate=20).to_c(12)
+    plan = _lib.DnPlan()
+    assert lib.dn_make_plan(C.byref(prm), 128, 1000, 128, 0, 148, 232448, C.byref(plan)) == 0
+    assert plan.tile == 2 and plan.threads == 128 and plan.resident_cols == 128 and plan.ws_cols == 0
+    assert plan.smem_bytes < 64 * 1024 and plan.ctas > 148
+    assert lib.dn_make_plan(C.byref(prm), 100000, 1000, -1, 0, 148, 232448, C.byref(plan)) == 0
+    assert 0 < plan.resident_cols < 100000 and plan.ws_cols >= 100000
+    bad = Params().to_c(1)
+    assert lib.dn_make_plan(C.byref(bad), 128, 10, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
+    assert b"2 samples" in lib.dn_last_error()
+    big = Params().to_c(500)
+    assert lib.dn_make_plan(C.byref(big), 128, 10, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_UNSUPPORTED
+
+
+def test_no_cpu_fallback():
+    """The product path refuses to run without a CUDA device instead of falling back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from collections import OrderedDict
+    from degnorm_b200 import GeneNMFOA
+    with pytest.raises(RuntimeError):
+        GeneNMFOA().run(OrderedDict(a=np.ones((3, 60))), np.ones((1, 3)))
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "degnorm_b200")):
+        for f in files:
+            if f.endswith(".py") or f.endswith(".cu") or f.endswith(".h"):
+                txt = open(os.path.join(root, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_helper_statics_match_reference_semantics():
+    from degnorm_b200 import GeneNMFOA
+    assert GeneNMFOA.shift_bins([[0, 1], [4, 5], [6, 7]], 1) == [[0, 1], [2, 3], [4, 5]]     # nmf.py:160-187
+    x = np.array([[0., 1., 10.], [0., 0.5, 2.]])
+    assert GeneNMFOA.get_high_coverage_idx(x).tolist() == [2]                                   # strict >, nmf.py:76
