@@ -75,6 +75,7 @@ struct KArgs {
     double *cov_rowsum;
     int resident_cols, ld_res;
     int ch, ldm, ks;
+    int ms_doubles;         // scratch: M tile (tiled Gram) or reduction scratch (register Gram)
     int g_in_smem;
     double *ws;             // per-CTA slabs
     long long ws_stride;    // doubles per CTA slab
@@ -87,7 +88,7 @@ struct Carve {
     long long small, red, binm, alive, ibuf, G, ms, xr, lr, resb, tb, total;   // offsets in doubles
 };
 
-__host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, int ldm, int resident_cols, int ld_res) {
+__host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, long long ms_doubles, int resident_cols, int ld_res) {
     Carve c;
     long long o = 0;
     c.small = o; o += (long long)N_SMALL * pp;
@@ -96,7 +97,7 @@ __host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, int ldm, in
     c.alive = o; o += DN_MAX_BINS / 2;
     c.ibuf = o;  o += 16;
     c.G = o;     o += g_in_smem ? (long long)pp * pp : 0;
-    c.ms = o;    o += (long long)pp * ldm;
+    c.ms = o;    o += ms_doubles;
     c.xr = o;    o += resident_cols > 0 ? (long long)p * ld_res : 0;
     c.lr = o;    o += resident_cols > 0 ? (long long)p * ld_res : 0;
     c.resb = o;  o += resident_cols > 0 ? ld_res : 0;
@@ -468,12 +469,180 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
     __syncthreads();
 }
 
-template <int NT>
+// ---- register-Gram pass for few samples (p <= P <= 12) ---------------------------------------------------------
+// Each thread owns whole columns (c = tid, tid + NT, ...): it keeps the column's x and lambda in registers, does the
+// multiplier update, and accumulates the column's contribution to all P(P+1)/2 Gram entries in registers -- no
+// shared-memory operand traffic and exactly p(p+1)/2 FMAs per column.  The per-thread partial Grams are then
+// reduced through a small shared scratch (16 entries x 32 lanes per round) and across warps.
+// Scratch layout (g.ms): [NW][16*33] per-warp transpose buffers, then [NW][NE] per-warp sums.
+constexpr int RED_ROUND = 16;
+__host__ __device__ constexpr int reg_scratch_doubles(int P, int NT) {
+    return (NT / 32) * (RED_ROUND * 33) + (NT / 32) * (P * (P + 1) / 2);
+}
+
+template <int P, int NT, bool UPDATE>
+__device__ void gram_pass_reg(const KArgs &a, Gene &g) {
+    constexpr int NE = P * (P + 1) / 2;
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = a.p;
+    const long long ld = g.ld;
+    double acc[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) acc[e] = 0.0;
+    double vv[P];
+#pragma unroll
+    for (int i = 0; i < P; ++i) vv[i] = (UPDATE && i < p) ? g.v[i] : 0.0;
+    const double c = a.c;
+    for (int vc = tid; vc < g.n_cur; vc += NT) {
+        const int pc = phys_col(g, vc);
+        const double *xc = g.X + pc;
+        double m[P];
+        if (!UPDATE) {
+#pragma unroll
+            for (int i = 0; i < P; ++i) m[i] = i < p ? xc[i * ld] : 0.0;
+        } else {
+            double *lc = g.Lm + pc;
+            double x[P], l[P];
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                x[i] = i < p ? xc[i * ld] : 0.0;
+                l[i] = i < p ? lc[i * ld] : 0.0;
+            }
+            double t = 0.0;
+#pragma unroll
+            for (int i = 0; i < P; ++i) t = fma(vv[i], x[i] + l[i], t);
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const double res = vv[i] * t - x[i];          // est - x
+                double ln = l[i] - c * res;
+                ln = ln < 0.0 ? 0.0 : ln;
+                if (i < p) lc[i * ld] = ln;
+                m[i] = x[i] + ln;
+            }
+        }
+        int e = 0;
+#pragma unroll
+        for (int i = 0; i < P; ++i)
+#pragma unroll
+            for (int j = i; j < P; ++j) {
+                acc[e] = fma(m[i], m[j], acc[e]);
+                ++e;
+            }
+    }
+    // warp-level transposed reduction, RED_ROUND entries per round; two lanes share one entry
+    double *sc = g.ms + warp * (RED_ROUND * 33);
+    double *part = g.ms + NW * (RED_ROUND * 33);
+    const int k = lane >> 1, h = lane & 1;
+#pragma unroll
+    for (int r0 = 0; r0 < NE; r0 += RED_ROUND) {
+#pragma unroll
+        for (int q = 0; q < RED_ROUND; ++q)
+            if (r0 + q < NE) sc[q * 33 + lane] = acc[r0 + q];
+        __syncwarp();
+        double s = 0.0;
+        const double *row = sc + k * 33 + h * 16;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) s += row[q];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (h == 0 && r0 + k < NE) part[warp * NE + r0 + k] = s;
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int e = tid; e < NE; e += NT) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += part[w * NE + e];
+        int i = 0, t = e;
+        while (t >= P - i) { t -= P - i; ++i; }
+        const int j = i + t;
+        g.G[i * P + j] = s;
+        g.G[j * P + i] = s;
+    }
+    __syncthreads();
+}
+
+// Power iteration for P <= 16 with the matrix row in registers (G is P x P in shared memory, row stride P).
+template <int P>
+__device__ int eig_warp_small(const double *G, int p, double *v, bool cold, int *conv) {
+    const int lane = threadIdx.x & 31;
+    const bool row_ok = lane < P;
+    double grow[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) grow[k] = row_ok ? G[lane * P + k] : 0.0;
+    double vi = 0.0;
+    if (cold) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) s += grow[k];
+        double n2 = s * s;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        n2 = __shfl_sync(0xffffffffu, n2, 0);
+        vi = n2 > 0.0 ? s * rsqrt(n2) : 0.0;
+        __syncwarp();
+        if (row_ok) v[lane] = vi;
+        __syncwarp();
+    } else {
+        if (row_ok) vi = v[lane];
+    }
+    int steps = 0, ok = 0;
+    double prev = 1.0e300;
+    for (; steps < EIG_FAST_STEPS;) {
+        double y = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) y = fma(grow[k], v[k], y);
+        ++steps;
+        double n2 = y * y;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        n2 = __shfl_sync(0xffffffffu, n2, 0);
+        if (!(n2 > 0.0)) {
+            __syncwarp();
+            if (row_ok) v[lane] = 0.0;
+            __syncwarp();
+            vi = 0.0;
+            ok = 1;
+            break;
+        }
+        const double w = y * rsqrt(n2);
+        double d = fabs(w - vi);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+        d = __shfl_sync(0xffffffffu, d, 0);
+        vi = w;
+        __syncwarp();
+        if (row_ok) v[lane] = w;
+        __syncwarp();
+        if (d <= EIG_TOL) { ok = 1; break; }
+        if (steps >= 8 && d > 0.75 * prev) break;
+        prev = d;
+    }
+    if (ok == 1) {                                  // warm-start distrust rule, see eig_warp
+        const double diag = row_ok ? G[lane * P + lane] : 0.0;
+        double m = (lane < p && diag > 0.0) ? vi : 1.0;
+        double mx = row_ok ? vi : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+            mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        m = __shfl_sync(0xffffffffu, m, 0);
+        mx = __shfl_sync(0xffffffffu, mx, 0);
+        if (m < EIG_SUSPECT * mx) ok = 2;
+    }
+    if (lane == 0) *conv = ok;
+    return steps;
+}
+
+template <int NT, int PREG>
 __device__ __forceinline__ void eig_solve(const KArgs &a, Gene &g, bool cold) {
     int conv = 1;
     if (a.g_in_smem) {
         if (threadIdx.x < 32) {
-            int s = eig_warp(g.G, a.pp, a.p, g.v, cold, g.ibuf + 12);
+            int s;
+            if constexpr (PREG > 0) s = eig_warp_small<PREG>(g.G, a.p, g.v, cold, g.ibuf + 12);
+            else s = eig_warp(g.G, a.pp, a.p, g.v, cold, g.ibuf + 12);
             g.eig_steps += s;
         }
         __syncthreads();
@@ -571,7 +740,7 @@ __device__ void final_pass(const KArgs &a, Gene &g, bool first, bool have_lambda
 }
 
 // nmf() on the current column set (nmf.py:78-107).  Leaves v, K, tmp=rs(KE), rsF, rsC, resb, tb.
-template <int TR, int NT>
+template <int TR, int NT, int PREG>
 __device__ void run_nmf(const KArgs &a, Gene &g, bool first, bool want_res, double *e_first_g, int ti, int tj, int ks,
                         bool tile_ok) {
     const int tid = threadIdx.x;
@@ -582,11 +751,13 @@ __device__ void run_nmf(const KArgs &a, Gene &g, bool first, bool want_res, doub
             for (int j = tid; j < g.n0; j += NT) g.Lm[(long long)i * g.ld + j] = 0.0;
         __syncthreads();
     }
-    gram_pass<TR, NT, false>(a, g, ti, tj, ks, tile_ok);
-    eig_solve<NT>(a, g, true);
+    if constexpr (PREG > 0) gram_pass_reg<PREG, NT, false>(a, g);
+    else gram_pass<TR, NT, false>(a, g, ti, tj, ks, tile_ok);
+    eig_solve<NT, PREG>(a, g, true);
     for (int it = 0; it < T; ++it) {
-        gram_pass<TR, NT, true>(a, g, ti, tj, ks, tile_ok);
-        eig_solve<NT>(a, g, false);
+        if constexpr (PREG > 0) gram_pass_reg<PREG, NT, true>(a, g);
+        else gram_pass<TR, NT, true>(a, g, ti, tj, ks, tile_ok);
+        eig_solve<NT, PREG>(a, g, false);
     }
     final_pass<NT>(a, g, first, T > 0, want_res, e_first_g);
 }
@@ -625,12 +796,12 @@ __device__ double median_one_minus(const double *rho, int p) {
     return 0.5 * (lo + hi);
 }
 
-template <int TR, int NT>
+template <int TR, int NT, int PREG>
 __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p, pp = a.pp;
-    const Carve cv = carve(p, pp, a.g_in_smem, a.ldm, a.resident_cols, a.ld_res);
+    const Carve cv = carve(p, pp, a.g_in_smem, a.ms_doubles, a.resident_cols, a.ld_res);
 
     Gene g;
     double *sm = smem + cv.small;
@@ -654,18 +825,19 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
     g.eig_fallbacks = 0;
 
     // Gram tile owned by this thread
-    const int ntg = pp / TR;
-    const int ntiles = ntg * (ntg + 1) / 2;
-    const int ks = tid / ntiles;
-    const bool tile_ok = ks < a.ks;
-    int ti = 0, tj = 0;
-    {
+    int ks = 0, ti = 0, tj = 0;
+    bool tile_ok = false;
+    if constexpr (PREG == 0) {
+        const int ntg = pp / TR;
+        const int ntiles = ntg * (ntg + 1) / 2;
+        ks = tid / ntiles;
+        tile_ok = ks < a.ks;
         int t = tid - ks * ntiles;
         while (t >= ntg - ti) { t -= ntg - ti; ++ti; }
         tj = ti + t;
     }
     // padded rows of the tile stay zero for the whole kernel
-    for (int e = tid; e < pp * a.ldm; e += NT) g.ms[e] = 0.0;
+    for (int e = tid; e < a.ms_doubles; e += NT) g.ms[e] = 0.0;
     for (int e = tid; e < N_SMALL * pp; e += NT) sm[e] = 0.0;
     __syncthreads();
 
@@ -695,7 +867,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
             g.tb = res_ok ? smem + cv.tb : slab + slab_o;
             g.resb = nullptr;
             if (L >= 2) {
-                run_nmf<TR, NT>(a, g, true, false, nullptr, ti, tj, ks, tile_ok);
+                run_nmf<TR, NT, PREG>(a, g, true, false, nullptr, ti, tj, ks, tile_ok);
                 if (tid < p) {
                     a.est_rowsum[(long long)gid * p + tid] = g.rsC[tid];
                     a.cov_rowsum[(long long)gid * p + tid] = g.rsF[tid];
@@ -810,7 +982,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
             } else {
                 const bool store_e = (a.e_first != nullptr) && (n0 == L);
                 // (4) first fit (nmf.py:245-254)
-                run_nmf<TR, NT>(a, g, true, true, store_e ? a.e_first + o0 : nullptr, ti, tj, ks, tile_ok);
+                run_nmf<TR, NT, PREG>(a, g, true, true, store_e ? a.e_first + o0 : nullptr, ti, tj, ks, tile_ok);
                 nmf_calls = 1; sum_cols = n0;
                 if (tid < p) {
                     g.rho[tid] = 1.0 - g.rs0[tid] / (g.tmp[tid] + 1.0);
@@ -857,7 +1029,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
                             g.n_cur -= wd;
                             drops |= 1ull << bd;
                             if (g.n_cur < 2) break;                      // svds ValueError swallowed, nmf.py:306-310
-                            run_nmf<TR, NT>(a, g, false, true, nullptr, ti, tj, ks, tile_ok);
+                            run_nmf<TR, NT, PREG>(a, g, false, true, nullptr, ti, tj, ks, tile_ok);
                             nmf_calls += 1; sum_cols += g.n_cur;
                             double mn = g.tmp[0];
                             for (int i = 1; i < p; ++i) mn = fmin(mn, g.tmp[i]);
@@ -1119,7 +1291,7 @@ __global__ void __launch_bounds__(256) init_apply_kernel(const double *sums, con
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
-int tile_for_p(int p) { return p <= 16 ? 2 : (p <= 64 ? 4 : 8); }
+int tile_for_p(int p) { return p <= 64 ? 4 : 8; }
 
 int check_params(const dn_params *prm) {
     if (!prm) return fail(DN_ERR_INVALID, "null params%s");
@@ -1131,37 +1303,72 @@ int check_params(const dn_params *prm) {
     return DN_OK;
 }
 
-struct Derived { int tr, nt, pp, ntiles, ch, ldm, ks, g_in_smem; long long fixed_doubles; };
+struct Derived { int tr, nt, preg, pp, ntiles, ch, ldm, ks, g_in_smem, ms_doubles; long long fixed_doubles; };
 
-Derived derive(int p) {
+// Threads per CTA of the register-Gram path, by resident tier: small genes get one warp per gene (no block-wide
+// barriers on the per-iteration critical path, many genes in flight per SM); larger tiers get more warps per gene
+// so that the shared-memory-limited CTAs still fill the SM.
+int threads_for_tier(int resident_cols) {
+    if (resident_cols <= 0) return 256;
+    if (resident_cols <= 128) return 32;
+    if (resident_cols <= 256) return 64;
+    if (resident_cols <= 512) return 128;
+    return 256;
+}
+
+Derived derive(int p, int nt_reg) {
     Derived d;
-    d.tr = tile_for_p(p);
-    d.nt = d.tr == 2 ? 128 : 256;
-    d.pp = (p + d.tr - 1) / d.tr * d.tr;
-    const int ntg = d.pp / d.tr;
-    d.ntiles = ntg * (ntg + 1) / 2;
-    int ch = (48 * 1024 / 8) / d.pp / 32 * 32;
-    if (ch < 32) ch = 32;
-    if (ch > d.nt) ch = d.nt;
-    d.ch = ch;
-    d.ldm = ch + 1;
-    int ks = d.nt / d.ntiles;
-    const long long cap = (long long)d.pp * d.ldm / ((long long)d.ntiles * d.tr * d.tr);
-    if (ks > cap) ks = (int)cap;
-    if (ks < 1) ks = 1;
-    d.ks = ks;
-    d.g_in_smem = d.pp <= 64;
-    d.fixed_doubles = carve(p, d.pp, d.g_in_smem, d.ldm, 0, 0).total;
+    memset(&d, 0, sizeof(d));
+    d.preg = p <= 4 ? 4 : (p <= 8 ? 8 : (p <= 12 ? 12 : 0));
+    if (d.preg > 0) {
+        d.tr = 0;
+        d.nt = nt_reg;
+        d.pp = d.preg;
+        d.ntiles = 0;
+        d.ch = 0; d.ldm = 0; d.ks = 1;
+        d.g_in_smem = 1;
+        d.ms_doubles = reg_scratch_doubles(d.preg, d.nt);
+    } else {
+        d.tr = tile_for_p(p);
+        d.nt = 256;
+        d.pp = (p + d.tr - 1) / d.tr * d.tr;
+        const int ntg = d.pp / d.tr;
+        d.ntiles = ntg * (ntg + 1) / 2;
+        int ch = (48 * 1024 / 8) / d.pp / 32 * 32;
+        if (ch < 32) ch = 32;
+        if (ch > d.nt) ch = d.nt;
+        d.ch = ch;
+        d.ldm = ch + 1;
+        int ks = d.nt / d.ntiles;
+        const long long cap = (long long)d.pp * d.ldm / ((long long)d.ntiles * d.tr * d.tr);
+        if (ks > cap) ks = (int)cap;
+        if (ks < 1) ks = 1;
+        d.ks = ks;
+        d.g_in_smem = d.pp <= 64;
+        d.ms_doubles = d.pp * d.ldm;
+    }
+    d.fixed_doubles = carve(p, d.pp, d.g_in_smem, d.ms_doubles, 0, 0).total;
     return d;
 }
 
-template <int TR, int NT>
+template <int TR, int NT, int PREG>
 int launch(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
-    auto kern = nmfoa_kernel<TR, NT>;
+    auto kern = nmfoa_kernel<TR, NT, PREG>;
     DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
     kern<<<plan->ctas, NT, plan->smem_bytes, st>>>(a);
     DN_CUDA(cudaGetLastError());
     return DN_OK;
+}
+
+template <int PREG>
+int launch_reg(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+    switch (plan->threads) {
+        case 32: return launch<0, 32, PREG>(a, plan, st);
+        case 64: return launch<0, 64, PREG>(a, plan, st);
+        case 128: return launch<0, 128, PREG>(a, plan, st);
+        case 256: return launch<0, 256, PREG>(a, plan, st);
+    }
+    return fail(DN_ERR_INVALID, "plan.threads must be 32, 64, 128 or 256%s");
 }
 
 int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
@@ -1173,7 +1380,7 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     if (!plan || !cov || !off || !order) return fail(DN_ERR_INVALID, "null pointer argument%s");
     if (n_work <= 0) return DN_OK;
     if (workspace_bytes < plan->ws_bytes || !workspace) return fail(DN_ERR_WORKSPACE, "workspace too small%s: need %lld, got %lld", "", plan->ws_bytes, workspace_bytes);
-    const Derived d = derive(prm->p);
+    const Derived d = derive(prm->p, plan->threads);
     if (plan->tile != d.tr || plan->threads != d.nt || plan->chunk_cols != d.ch)
         return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1190,7 +1397,7 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     a.est_rowsum = est_rowsum; a.cov_rowsum = cov_rowsum;
     a.resident_cols = plan->resident_cols;
     a.ld_res = plan->resident_cols;
-    a.ch = d.ch; a.ldm = d.ldm; a.ks = d.ks; a.g_in_smem = d.g_in_smem;
+    a.ch = d.ch; a.ldm = d.ldm; a.ks = d.ks; a.g_in_smem = d.g_in_smem; a.ms_doubles = d.ms_doubles;
     // workspace: [queue (256 B)] [per-CTA slabs]
     a.queue = (int *)workspace;
     a.ws = (double *)((char *)workspace + 256);
@@ -1199,9 +1406,11 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     const long long cols_d = mode == MODE_INIT ? plan->ws_cols : (2ll * prm->p + 2) * plan->ws_cols;
     a.ws_stride = (g_d + cols_d + 31) / 32 * 32;
     DN_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
-    if (d.tr == 2) return launch<2, 128>(a, plan, st);
-    if (d.tr == 4) return launch<4, 256>(a, plan, st);
-    return launch<8, 256>(a, plan, st);
+    if (d.preg == 4) return launch_reg<4>(a, plan, st);
+    if (d.preg == 8) return launch_reg<8>(a, plan, st);
+    if (d.preg == 12) return launch_reg<12>(a, plan, st);
+    if (d.tr == 4) return launch<4, 256, 0>(a, plan, st);
+    return launch<8, 256, 0>(a, plan, st);
 }
 
 }  // namespace
@@ -1230,7 +1439,10 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
     int rc = check_params(prm);
     if (rc) return rc;
     if (!plan || max_cols < 1 || sm_count < 1 || max_smem_optin < 16 * 1024) return fail(DN_ERR_INVALID, "bad planning argument%s");
-    const Derived d = derive(prm->p);
+    // register-Gram path: the CTA size follows the resident tier that was asked for
+    const int want_cols = want_resident < 0 ? (max_cols > 1 << 20 ? 1 << 20 : (int)max_cols)
+                                             : (want_resident > max_cols ? (int)max_cols : want_resident);
+    const Derived d = derive(prm->p, for_init ? 256 : threads_for_tier(want_cols));
     if (d.ntiles > d.nt) return fail(DN_ERR_UNSUPPORTED, "%sp = %lld needs more Gram tiles than threads", "", prm->p);
     memset(plan, 0, sizeof(*plan));
     plan->tile = d.tr;
@@ -1254,7 +1466,8 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
     // persistent CTAs: as many as the shared memory / thread budget of an SM allows
     int per_sm = (int)((228ll * 1024) / (plan->smem_bytes + 1024));
     if (per_sm > 2048 / d.nt) per_sm = 2048 / d.nt;
-    if (per_sm > 8) per_sm = 8;
+    if (per_sm > 32) per_sm = 32;
+    if (d.preg == 12 && per_sm * d.nt > 256) per_sm = 256 / d.nt > 0 ? 256 / d.nt : 1;   // ~250 registers per thread
     if (per_sm < 1) per_sm = 1;
     long long ctas = (long long)sm_count * per_sm;
     if (ctas > n_work) ctas = n_work;
