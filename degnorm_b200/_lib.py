@@ -6,12 +6,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdegnorm_b200.so")
 
+ABI_VERSION = 2
 DN_NCOUNTERS = 8
 DN_MAX_BINS = 64
 DN_MAX_SAMPLES = 128
 CNT_EXIT, CNT_N_HICOV, CNT_NMF_CALLS, CNT_SUM_COLS, CNT_EIG_STEPS, CNT_DROPS_LO, CNT_DROPS_HI, CNT_RESIDENT = range(8)
 EXIT_NAMES = {0: "none", 1: "few_hicov", 2: "empty_sample", 3: "median", 4: "no_selection", 5: "refined",
-              6: "fallback_high", 7: "fallback"}
+              6: "fallback_high", 7: "fallback", -1: "plan_error"}
 
 DN_ERR_INVALID, DN_ERR_CUDA, DN_ERR_UNSUPPORTED, DN_ERR_WORKSPACE = -1, -2, -3, -4
 
@@ -39,11 +40,11 @@ _SIGS = {
     "dn_last_error": (C.c_char_p, []),
     "dn_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3),
     "dn_make_plan": (C.c_int, [C.POINTER(DnParams), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                               C.POINTER(DnPlan)]),
-    "dn_init_ratio_svd": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P,
+                               C.c_int32, C.POINTER(DnPlan)]),
+    "dn_init_ratio_svd": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P, _P,
                                     C.c_int64, _P]),
     "dn_baseline_selection": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P,
-                                        _P, _P, _P, _P, C.c_int64, _P]),
+                                        _P, _P, _P, _P, _P, C.c_int64, _P]),
     "dn_estimates": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), _P, _P, _P, _P, _P, _P]),
     "dn_outer_sums": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
     "dn_outer_apply": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),
@@ -66,7 +67,7 @@ def lib():
             f = getattr(l, name)
             f.restype = res
             f.argtypes = args
-        if l.dn_abi_version() != 1:
+        if l.dn_abi_version() != ABI_VERSION:
             raise ImportError("degnorm_b200: ABI version mismatch")
         _lib = l
     return _lib

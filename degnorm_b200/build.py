@@ -5,10 +5,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-SRC = [os.path.join(HERE, "csrc", "nmfoa_kernels.cu")]
+CSRC = os.path.join(HERE, "csrc")
+SRC = [os.path.join(CSRC, f) for f in ("abi.cu", "nmfoa_tiled.cu", "nmfoa_small_p4.cu", "nmfoa_small_p8.cu",
+                                       "nmfoa_small_p12.cu")]
+HDR = [os.path.join(CSRC, f) for f in ("common.cuh", "launch.h", "nmfoa_small.cuh")]
+OBJ = os.path.join(HERE, "csrc", "_build")
 OUT = os.path.join(HERE, "libdegnorm_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include")]
 
 
@@ -16,19 +20,41 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = SRC + [os.path.join(ROOT, "include", "degnorm_b200.h")]
+    deps = SRC + HDR + [os.path.join(ROOT, "include", "degnorm_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _compile(args):
+    src, obj, verbose = args
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r.returncode, r.stdout + r.stderr
+
+
 def build(force=False, verbose=False):
+    """One nvcc per translation unit, in parallel; objects whose source and headers are unchanged are re-used."""
     if not force and not needs_build():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRC
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in HDR + [os.path.join(ROOT, "include", "degnorm_b200.h")])
+    jobs, objs = [], []
+    for s in SRC:
+        o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
+            jobs.append((s, o, verbose))
+    with ThreadPoolExecutor(max_workers=max(1, len(jobs))) as ex:
+        for src, rc, log in ex.map(_compile, jobs):
+            if verbose or rc != 0:
+                sys.stderr.write("== %s\n%s" % (os.path.basename(src), log))
+            if rc != 0:
+                raise RuntimeError("nvcc failed on %s" % src)
+    r = subprocess.run([NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building %s" % OUT)
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed linking %s" % OUT)
     return OUT
 
 

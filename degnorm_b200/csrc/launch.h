@@ -1,0 +1,99 @@
+// degnorm_b200 -- launch geometry shared by the host planner (abi.cu) and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+// ---- tiled kernel (any p; nmfoa_tiled.cu): shared-memory carve-up ---------------------------------------------
+struct Carve {
+    long long small, red, binm, alive, ibuf, G, ms, xr, lr, resb, tb, total;   // offsets in doubles
+};
+
+__host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, long long ms_doubles, int resident_cols, int ld_res) {
+    Carve c;
+    long long o = 0;
+    c.small = o; o += (long long)N_SMALL * pp;
+    c.red = o;   o += 64;
+    c.binm = o;  o += DN_MAX_BINS;
+    c.alive = o; o += DN_MAX_BINS / 2;
+    c.ibuf = o;  o += 16;
+    c.G = o;     o += g_in_smem ? (long long)pp * pp : 0;
+    c.ms = o;    o += ms_doubles;
+    c.xr = o;    o += resident_cols > 0 ? (long long)p * ld_res : 0;
+    c.lr = o;    o += resident_cols > 0 ? (long long)p * ld_res : 0;
+    c.resb = o;  o += resident_cols > 0 ? ld_res : 0;
+    c.tb = o;    o += resident_cols > 0 ? ld_res : 0;
+    c.total = o;
+    return c;
+}
+
+struct Derived { int tr, nt, pp, ntiles, ch, ldm, ks, g_in_smem, ms_doubles; long long fixed_doubles; };
+
+inline int tile_for_p(int p) { return p <= 64 ? 4 : 8; }
+
+inline Derived derive(int p) {
+    Derived d;
+    memset(&d, 0, sizeof(d));
+    d.tr = tile_for_p(p);
+    d.nt = 256;
+    d.pp = (p + d.tr - 1) / d.tr * d.tr;
+    const int ntg = d.pp / d.tr;
+    d.ntiles = ntg * (ntg + 1) / 2;
+    int ch = (48 * 1024 / 8) / d.pp / 32 * 32;
+    if (ch < 32) ch = 32;
+    if (ch > d.nt) ch = d.nt;
+    d.ch = ch;
+    d.ldm = ch + 1;
+    int ks = d.nt / d.ntiles;
+    const long long cap = (long long)d.pp * d.ldm / ((long long)d.ntiles * d.tr * d.tr);
+    if (ks > cap) ks = (int)cap;
+    if (ks < 1) ks = 1;
+    d.ks = ks;
+    d.g_in_smem = d.pp <= 64;
+    d.ms_doubles = d.pp * d.ldm;
+    d.fixed_doubles = carve(p, d.pp, d.g_in_smem, d.ms_doubles, 0, 0).total;
+    return d;
+}
+
+// ---- small-p kernel (p <= 12; nmfoa_small.cuh): column-major x / M with a padded column stride ----------------
+// P = p rounded up to 4, 8 or 12 (0: not on this path).  A column holds P doubles + 2 of padding so that a warp
+// reading one column per lane with 128-bit loads touches every bank exactly once (stride = 4 mod 8 words).
+__host__ __device__ inline int small_P(int p) { return p <= 4 ? 4 : (p <= 8 ? 8 : (p <= 12 ? 12 : 0)); }
+__host__ __device__ inline int small_cs(int P) { return P + 2; }
+constexpr int SMALL_GPART = 96;       // doubles per warp of partial Gram / reduction scratch
+constexpr int SMALL_MAX_WARPS = 16;
+
+struct SmallCarve {
+    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, X, M, resb, tb, total;   // offsets in doubles
+};
+
+__host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_cols) {
+    SmallCarve c;
+    long long o = 0;
+    c.small = o; o += (long long)N_SMALL * P;
+    c.red = o;   o += 64;
+    c.binm = o;  o += DN_MAX_BINS;
+    c.alive = o; o += DN_MAX_BINS / 2;
+    c.ibuf = o;  o += 16;
+    c.G = o;     o += (long long)P * P;
+    c.vx = o;    o += (long long)nw * 2 * P;
+    c.gpart = o; o += (long long)nw * SMALL_GPART;
+    c.tab = o;   o += 32;                       // 16 tiles x 4 ints
+    const long long cs = small_cs(P);
+    c.X = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
+    c.M = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
+    c.resb = o;  o += resident_cols > 0 ? resident_cols : 0;
+    c.tb = o;    o += resident_cols > 0 ? resident_cols : 0;
+    c.total = o;
+    return c;
+}
+
+// per-CTA global slab of the small path (doubles): eigen fallback scratch + streamed column storage
+__host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols) {
+    const long long d = 2ll * P * P + (2ll * small_cs(P) + 2) * ws_cols;
+    return (d + 31) / 32 * 32;
+}
+
+// launchers (each defined in its own translation unit)
+int dn_launch_tiled(const KArgs &a, const dn_plan *plan, cudaStream_t st);
+int dn_launch_small4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
+int dn_launch_small8(const KArgs &a, const dn_plan *plan, cudaStream_t st);
+int dn_launch_small12(const KArgs &a, const dn_plan *plan, cudaStream_t st);

@@ -1,0 +1,749 @@
+// degnorm_b200 -- fused baseline-selection kernel for few samples (p <= 12), sm_100a.
+//
+// Same per-gene flow as nmfoa_tiled.cu (reference: /root/reference/degnorm/nmf.py:189-372 around nmf.py:78-107),
+// re-laid-out for the regime where a gene has tens to a few hundred kept columns and the cost is instruction
+// latency, not bytes:
+//
+//   * x and M = x + lambda live column-major with a padded column stride (P + 2 doubles), in shared memory
+//     (resident tiers) or in a per-CTA global slab (streamed tier).  lambda itself is never stored:
+//     lambda = M - x is recovered on load (exact when lambda = 0; otherwise within half an ulp of M).
+//   * one inner iteration (nmf.py:93-98) = phase A, one lane per column: t = v.M_j, lambda update, new M_j;
+//     phase B, lanes own 2 x TC tiles of the Gram matrix and sweep the columns their own warp just wrote
+//     (operands come straight from shared memory: no cross-lane reduction of P(P+1)/2 partial sums);
+//     a k-slice reduction over 2..8 lanes, a cross-warp sum for multi-warp CTAs; then the P x P eigen-solve.
+//   * the eigen-solve keeps the matrix row and the whole vector in registers; steps exchange the new vector
+//     through a warp-private shared buffer (one store, one __syncwarp, P/2 128-bit loads).  Warm solves run
+//     `hint - 1` un-normalised steps blind (scaled by the last 1/lambda_1) before the first checked step; the hint
+//     adapts to the step count the previous solve of the same nmf() call needed.  Every warp of a CTA solves
+//     redundantly, so no barrier separates the solve from the next phase A.
+//   * dropping a bin physically rotates its columns to the end of the buffer, so the current matrix is always the
+//     contiguous range [0, n_cur): no per-column index mapping in the inner loop.
+//
+// No tensor cores: fp64 FMA pipe only.
+#pragma once
+#include "common.cuh"
+#include "launch.h"
+
+namespace {
+
+template <int P> struct SmallCfg;
+// TC: tile columns (tile = 2 rows x TC columns of G), NTILE tiles cover the upper triangle, NTP = tiles padded
+// to a power of two, KS = k-slices (lanes = NTP * KS)
+template <> struct SmallCfg<12> { static constexpr int TC = 3, NTILE = 16, NTP = 16, KS = 2; };
+template <> struct SmallCfg<8> { static constexpr int TC = 2, NTILE = 10, NTP = 16, KS = 2; };
+template <> struct SmallCfg<4> { static constexpr int TC = 2, NTILE = 3, NTP = 4, KS = 8; };
+
+template <int NW>
+__device__ __forceinline__ void bsync() {
+    if constexpr (NW == 1) __syncwarp();
+    else __syncthreads();
+}
+
+struct SGene {
+    double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *vx, *gpart;
+    int *alive, *ibuf, *tab;
+    double *X, *M, *resb, *tb;
+    int n0, n_cur, cs, nb0, nalive;
+    int eig_steps, eig_fallbacks;
+    double *B0;
+    int r0, offA, offB, ks, u0, u1, u2;     // this lane's Gram tile
+    bool tile_ok;
+};
+
+template <int P>
+__device__ __forceinline__ void tile_of(int t, int &r0, int &c0, bool &ok) {
+    constexpr int TC = SmallCfg<P>::TC;
+    int idx = 0;
+    ok = false; r0 = 0; c0 = 0;
+    for (int rb = 0; rb < P / 2; ++rb)
+        for (int cb = 0; cb < P / TC; ++cb)
+            if (cb * TC + TC - 1 >= 2 * rb) {
+                if (idx == t) { r0 = 2 * rb; c0 = cb * TC; ok = true; }
+                ++idx;
+            }
+}
+
+template <int P>
+__device__ __forceinline__ void load_col(const double *base, double (&x)[P]) {
+    const double2 *q = reinterpret_cast<const double2 *>(base);
+#pragma unroll
+    for (int i = 0; i < P / 2; ++i) {
+        const double2 t = q[i];
+        x[2 * i] = t.x;
+        x[2 * i + 1] = t.y;
+    }
+}
+
+template <int P>
+__device__ __forceinline__ double dot_v(const double (&v)[P], const double (&m)[P]) {
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; i += 2) {
+        t0 = fma(v[i], m[i], t0);
+        t1 = fma(v[i + 1], m[i + 1], t1);
+    }
+    return t0 + t1;
+}
+
+// sums NV per-thread values over the CTA (fixed tree: warp shuffles, then warps in order) into out[0..NV)
+template <int NV, int NW>
+__device__ __forceinline__ void block_sum_vec(double (&x)[NV], double *part, double *out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x[k] = warp_sum(x[k]);
+    if constexpr (NW == 1) {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) out[k] = x[k];
+        }
+        __syncwarp();
+    } else {
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) part[warp * NV + k] = x[k];
+        }
+        __syncthreads();
+        for (int k = tid; k < NV; k += NW * 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += part[w * NV + k];
+            out[k] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- one pass: (optional multiplier update of this warp's columns) + Gram of M -----------------------------------
+// UPDATE=false: G = M M^T with M = x (first rank-one fit, nmf.py:88).
+// UPDATE=true : lambda <- max(0, lambda - c (K E - x)), M = x + lambda, G = M M^T (nmf.py:93-98); K E = v (v.M_old).
+template <int P, int NW, bool UPDATE>
+__device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const double (&v)[P]) {
+    using Cfg = SmallCfg<P>;
+    constexpr int TC = Cfg::TC, KS = Cfg::KS, NTP = Cfg::NTP, NTILE = Cfg::NTILE, CS = P + 2, NT = NW * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = g.n_cur;
+    const double c = a.c;
+    double acc[2][TC];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 0; q < TC; ++q) acc[r][q] = 0.0;
+
+    for (int b0 = warp * 32; b0 < n; b0 += NT) {
+        if constexpr (UPDATE) {
+            const int col = b0 + lane;
+            if (col < n) {
+                double x[P], m[P];
+                load_col<P>(g.X + col * CS, x);
+                load_col<P>(g.M + col * CS, m);
+                const double t = dot_v<P>(v, m);
+#pragma unroll
+                for (int i = 0; i < P; ++i) {
+                    const double res = fma(v[i], t, -x[i]);        // est - x
+                    double lam = m[i] - x[i];
+                    lam = fma(-c, res, lam);
+                    lam = lam < 0.0 ? 0.0 : lam;
+                    m[i] = x[i] + lam;
+                }
+                double2 *mq = reinterpret_cast<double2 *>(g.M + col * CS);
+#pragma unroll
+                for (int i = 0; i < P / 2; ++i) mq[i] = make_double2(m[2 * i], m[2 * i + 1]);
+            }
+            __syncwarp();
+        }
+        if (g.tile_ok) {
+            const int cend = min(b0 + 32, n);
+            const double *mc = g.M + (b0 + g.ks) * CS;
+#pragma unroll 4
+            for (int col = b0 + g.ks; col < cend; col += KS, mc += KS * CS) {
+                const double2 ar = *reinterpret_cast<const double2 *>(mc + g.r0);
+                const double2 ua = *reinterpret_cast<const double2 *>(mc + g.offA);
+                acc[0][0] = fma(ar.x, ua.x, acc[0][0]);
+                acc[0][1] = fma(ar.x, ua.y, acc[0][1]);
+                acc[1][0] = fma(ar.y, ua.x, acc[1][0]);
+                acc[1][1] = fma(ar.y, ua.y, acc[1][1]);
+                if constexpr (TC == 3) {
+                    const double ub = mc[g.offB];
+                    acc[0][2] = fma(ar.x, ub, acc[0][2]);
+                    acc[1][2] = fma(ar.y, ub, acc[1][2]);
+                }
+            }
+        }
+    }
+    // k-slice reduction (lane = ks * NTP + tile)
+#pragma unroll
+    for (int o = NTP; o < 32; o <<= 1)
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < TC; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], o);
+
+    if constexpr (NW == 1) {
+        if (g.ks == 0 && g.tile_ok) {
+            const int uu[3] = {g.u0, g.u1, g.u2};
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int q = 0; q < TC; ++q) {
+                    const int i = g.r0 + r, j = uu[q];
+                    if (i <= j) {
+                        g.G[i * P + j] = acc[r][q];
+                        g.G[j * P + i] = acc[r][q];
+                    }
+                }
+        }
+        __syncwarp();
+    } else {
+        if (g.ks == 0 && g.tile_ok) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int q = 0; q < TC; ++q) g.gpart[warp * SMALL_GPART + lane * (2 * TC) + r * TC + q] = acc[r][q];
+        }
+        __syncthreads();
+        for (int e = tid; e < NTILE * 2 * TC; e += NT) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += g.gpart[w * SMALL_GPART + e];
+            const int t = e / (2 * TC), rq = e - t * (2 * TC);
+            const int r = rq / TC, q = rq - r * TC;
+            const int i = g.tab[t * 4] + r, j = g.tab[t * 4 + 1 + q];
+            if (i <= j) {
+                g.G[i * P + j] = s;
+                g.G[j * P + i] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- top eigenvector of G (P x P in shared memory), every warp redundantly ------------------------------------
+// v: whole vector in registers (in: warm start unless cold; out: unit-norm eigenvector, or 0 for a zero matrix).
+// inv_lam: 1 / lambda_1 from the last checked step; hint: steps the previous solve needed.
+template <int P, int NW>
+__device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[P], bool cold, double &inv_lam, int &hint) {
+    constexpr int NT = NW * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *vx = g.vx + warp * (2 * P);
+    const int row = lane % P;
+    double grow[P];
+    load_col<P>(g.G + row * P, grow);
+    int par = 0;
+    // y = scale * G v, exchanged through the warp-private buffer (double-buffered: one __syncwarp per step)
+    auto step = [&](double scale) {
+        const double y = dot_v<P>(grow, v) * scale;
+        if (lane < P) vx[par * P + lane] = y;
+        __syncwarp();
+        load_col<P>(vx + par * P, v);
+        par ^= 1;
+    };
+    int steps = 0, ok = 0, checked = 0;
+    if (cold) {
+        // start from G.1 (row sums): positive for non-negative G, close to the Perron vector for near-rank-1 data
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) s += grow[k];
+        if (lane < P) vx[par * P + lane] = s;
+        __syncwarp();
+        load_col<P>(vx + par * P, v);
+        par ^= 1;
+    } else if (a.eig_hint && hint > 1) {
+        for (int b = 0; b < hint - 1; ++b) step(inv_lam);
+        steps = hint - 1;
+    }
+    if (cold || steps > 0) {
+        double n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) n2 = fma(v[k], v[k], n2);
+        const double inv = n2 > 0.0 ? rsqrt(n2) : 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) v[k] *= inv;
+    }
+    double prev = 1.0e300, d = 0.0;
+    for (; steps < EIG_FAST_STEPS;) {
+        double old[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) old[k] = v[k];
+        step(1.0);
+        ++steps;
+        ++checked;
+        double n2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) n2 = fma(v[k], v[k], n2);
+        if (!(n2 > 0.0)) {            // all-zero matrix: the reference raises ArpackError here
+#pragma unroll
+            for (int k = 0; k < P; ++k) v[k] = 0.0;
+            ok = 1;
+            break;
+        }
+        const double inv = rsqrt(n2);
+        d = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            v[k] *= inv;
+            d = fmax(d, fabs(v[k] - old[k]));
+        }
+        inv_lam = inv;
+        if (d <= EIG_TOL) { ok = 1; break; }
+        if (checked >= 2 && steps >= 8 && d > 0.75 * prev) break;     // small spectral gap: squaring solver
+        prev = d;
+    }
+    if (ok == 1) {
+        // warm-start distrust rule (see nmfoa_tiled.cu eig_warp): an entry ~0 on a sample that has coverage
+        double vmin = 1.0e300, vmax = 0.0;
+#pragma unroll
+        for (int k = 0; k < P; ++k) {
+            if (k < a.p) vmin = fmin(vmin, v[k]);
+            vmax = fmax(vmax, v[k]);
+        }
+        if (vmin < EIG_SUSPECT * vmax) {
+            vmin = 1.0e300;
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (k < a.p && g.G[k * P + k] > 0.0) vmin = fmin(vmin, v[k]);
+            if (vmin < EIG_SUSPECT * vmax) ok = 2;
+        }
+    }
+    g.eig_steps += steps;
+    if (ok == 1) {
+        if (checked == 1 && d <= 0.02 * EIG_TOL) hint = steps > 1 ? steps - 1 : 1;
+        else hint = steps;
+    } else {                                       // uniform across the CTA (every warp solved the same matrix)
+        if constexpr (NW > 1) __syncthreads();
+        int s = eig_squaring<NT>(g.G, P, a.p, g.v, g.red, g.B0, g.B0 + P * P, ok == 2);
+        g.eig_steps += s;
+        g.eig_fallbacks += 1;
+        load_col<P>(g.v, v);
+        bsync<NW>();
+        hint = 0;
+    }
+}
+
+// ---- final pass of an nmf() call (see final_pass in nmfoa_tiled.cu for what each sum is) ----------------------
+template <int P, int NW>
+__device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P], bool first, bool want_res,
+                                 double *e_first_g) {
+    constexpr int NT = NW * 32, CS = P + 2, NV = 2 + 2 * P;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = g.n_cur;
+    double acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+    for (int col = tid; col < n; col += NT) {
+        double x[P], m[P];
+        load_col<P>(g.X + col * CS, x);
+        load_col<P>(g.M + col * CS, m);
+        const double t = dot_v<P>(v, m);
+        g.tb[col] = t;
+        acc[0] += t;
+        acc[1] = fma(t, t, acc[1]);
+        double r = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const double ke = v[i] * t;
+            const double kc = ke < x[i] ? x[i] : ke;
+            acc[2 + i] += x[i];
+            acc[2 + P + i] += kc;
+            if (want_res) {
+                const double q = ((first ? ke : kc) - x[i]) / (x[i] + 1.0);
+                r = fmax(r, q * q);
+            }
+        }
+        if (want_res) g.resb[col] = r;
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < P; ++k)
+            if (lane == k) g.v[k] = v[k];
+    }
+    block_sum_vec<NV, NW>(acc, g.gpart, g.red);       // (its barriers also publish tb / resb / v)
+    const double sum_t = g.red[0], sum_t2 = g.red[1];
+    const double sigma = sqrt(sum_t2);
+    if (e_first_g != nullptr) {                          // E of the first fit (only when no column was filtered)
+        const double inv = sigma > 0.0 ? 1.0 / sigma : 0.0;
+        for (int col = tid; col < n; col += NT) e_first_g[col] = g.tb[col] * inv;
+    }
+    if (tid < P) {
+        const double vi = g.v[tid];
+        g.rsF[tid] = g.red[2 + tid];
+        g.rsC[tid] = g.red[2 + P + tid];
+        g.tmp[tid] = vi * sum_t;          // rs(K E), unclamped
+        g.K[tid] = vi * sigma;            // K = u * s >= 0
+    }
+    bsync<NW>();
+}
+
+// nmf() on the current columns [0, n_cur) (nmf.py:78-107).  Leaves v, K, tmp = rs(KE), rsF, rsC, resb, tb.
+template <int P, int NW>
+__device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_res, double *e_first_g) {
+    constexpr int NT = NW * 32, CS = P + 2;
+    const int tid = threadIdx.x;
+    {   // lambda = 0: M = x
+        const double2 *src = reinterpret_cast<const double2 *>(g.X);
+        double2 *dst = reinterpret_cast<double2 *>(g.M);
+        const int n2 = g.n_cur * (CS / 2);
+        for (int e = tid; e < n2; e += NT) dst[e] = src[e];
+    }
+    bsync<NW>();
+    double v[P];
+#pragma unroll
+    for (int k = 0; k < P; ++k) v[k] = 0.0;
+    double inv_lam = 1.0;
+    int hint = 0;
+    gram_small<P, NW, false>(a, g, v);
+    eig_small<P, NW>(a, g, v, true, inv_lam, hint);
+    const int T = a.nmf_iter;
+    for (int it = 0; it < T; ++it) {
+        gram_small<P, NW, true>(a, g, v);
+        eig_small<P, NW>(a, g, v, false, inv_lam, hint);
+    }
+    final_pass_small<P, NW>(a, g, v, first, want_res, e_first_g);
+}
+
+template <int P, int NW, bool RES>
+__global__ void __launch_bounds__(NW * 32, 16 / NW) nmfoa_small_kernel(const KArgs a) {
+    extern __shared__ double smem[];
+    using Cfg = SmallCfg<P>;
+    constexpr int NT = NW * 32, CS = P + 2, TC = Cfg::TC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = a.p;
+    const SmallCarve cv = small_carve(P, NW, RES ? a.resident_cols : 0);
+
+    SGene g;
+    double *sm = smem + cv.small;
+    g.v = sm;           g.K = sm + P;        g.K0 = sm + 2 * P;   g.rs0 = sm + 3 * P;   g.rsF = sm + 4 * P;
+    g.rsC = sm + 5 * P; g.rsC0 = sm + 6 * P; g.rho = sm + 7 * P;  g.scale = sm + 8 * P; g.tmp = sm + 9 * P;
+    g.red = smem + cv.red;
+    g.binm = smem + cv.binm;
+    g.alive = reinterpret_cast<int *>(smem + cv.alive);
+    g.ibuf = reinterpret_cast<int *>(smem + cv.ibuf);
+    g.G = smem + cv.G;
+    g.vx = smem + cv.vx;
+    g.gpart = smem + cv.gpart;
+    g.tab = reinterpret_cast<int *>(smem + cv.tab);
+    double *slab = a.ws + (long long)blockIdx.x * a.ws_stride;
+    g.B0 = slab;
+    const int cap = RES ? a.resident_cols : (int)a.ws_ld;
+    if constexpr (RES) {
+        g.X = smem + cv.X; g.M = smem + cv.M; g.resb = smem + cv.resb; g.tb = smem + cv.tb;
+    } else {
+        g.X = slab + 2 * P * P;
+        g.M = g.X + (long long)CS * a.ws_ld;
+        g.resb = g.M + (long long)CS * a.ws_ld;
+        g.tb = g.resb + a.ws_ld;
+    }
+    {   // this lane's Gram tile; table of all tiles for the cross-warp sum
+        const int t = lane % Cfg::NTP;
+        g.ks = lane / Cfg::NTP;
+        int r0, c0;
+        bool ok;
+        tile_of<P>(t, r0, c0, ok);
+        g.tile_ok = ok;
+        g.r0 = r0;
+        if (TC == 3 && ((c0 / 3) & 1)) { g.offA = c0 + 1; g.offB = c0; g.u0 = c0 + 1; g.u1 = c0 + 2; g.u2 = c0; }
+        else { g.offA = c0; g.offB = c0 + 2; g.u0 = c0; g.u1 = c0 + 1; g.u2 = c0 + 2; }
+        if (tid < Cfg::NTP) {
+            g.tab[tid * 4] = g.r0; g.tab[tid * 4 + 1] = g.u0; g.tab[tid * 4 + 2] = g.u1; g.tab[tid * 4 + 3] = g.u2;
+        }
+    }
+    for (int e = tid; e < N_SMALL * P; e += NT) sm[e] = 0.0;
+    g.eig_steps = 0;
+    g.eig_fallbacks = 0;
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) g.ibuf[0] = atomicAdd(a.queue, 1);
+        __syncthreads();
+        const int w = g.ibuf[0];
+        __syncthreads();
+        if (w >= a.n_work) break;
+        const int gid = a.order[w];
+        const long long o0 = a.off[gid];
+        const int L = (int)(a.off[gid + 1] - o0);
+        const double *F = a.cov + (long long)p * o0;
+        int *cnt = a.counters ? a.counters + (long long)gid * DN_NCOUNTERS : nullptr;
+        g.eig_steps = 0;
+        g.eig_fallbacks = 0;
+
+        // ------------------------------------------------------------------ baseline_selection (nmf.py:189-372)
+        if (tid < P) g.scale[tid] = tid < p ? a.scale[tid] : 1.0;
+        __syncthreads();
+        // (1) matrix max of the scaled coverage: max_j (F_ij / s_i) = (max_j F_ij) / s_i  (division is monotone)
+        double tmax = -1.0e300;
+        if (a.row_max) {
+            if (tid < p) tmax = a.row_max[(long long)gid * p + tid] / g.scale[tid];
+        } else {
+            for (int i = 0; i < p; ++i) {
+                const double *row = F + (long long)i * L;
+                double m = -1.0e300;
+                for (int j = tid; j < L; j += NT) m = fmax(m, row[j]);
+                tmax = fmax(tmax, m / g.scale[i]);
+            }
+        }
+        const double gmax = block_max<NT>(tmax, g.red);
+        const double thr = 0.1 * gmax;                                   // nmf.py:76
+        // (2) keep the columns that are high coverage (strict >) and on the systematic sample (nmf.py:220-229),
+        //     scaled, compacted in order into the working buffer
+        const int rate = a.rate;
+        const int start = (rate > 1 && a.ds_start) ? a.ds_start[gid] : 0;
+        const int ncand = start < L ? (L - start + rate - 1) / rate : 0;
+        int exit_code = DN_EXIT_NONE;
+        int ran = 0, nmf_calls = 0, sum_cols = 0;
+        unsigned long long drops = 0ull;
+        bool k_is_refined = false;
+        int n0 = 0;
+        if (ncand > cap) {
+            exit_code = -1;                    // planner error: the bucket's tier is too small for this gene
+        } else {
+            int running = 0;
+            int *wcount = g.ibuf + 1;        // NW ints
+            for (int kb = 0; kb < ncand; kb += NT) {
+                const int k = kb + tid;
+                bool keep = false;
+                double xv[P];
+#pragma unroll
+                for (int i = 0; i < P; ++i) xv[i] = 0.0;
+                if (k < ncand) {
+                    const long long col = start + (long long)k * rate;
+                    double cm = -1.0e300;
+#pragma unroll
+                    for (int i = 0; i < P; ++i)
+                        if (i < p) {
+                            xv[i] = F[(long long)i * L + col] / g.scale[i];
+                            cm = fmax(cm, xv[i]);
+                        }
+                    keep = cm > thr;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                int pre = running, tot;
+                if constexpr (NW == 1) {
+                    tot = __popc(bal);
+                } else {
+                    if (lane == 0) wcount[warp] = __popc(bal);
+                    __syncthreads();
+                    tot = 0;
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) {
+                        const int cq = wcount[q];
+                        if (q < warp) pre += cq;
+                        tot += cq;
+                    }
+                }
+                if (keep) {
+                    const int dst = pre + __popc(bal & ((1u << lane) - 1u));
+                    double2 *xq = reinterpret_cast<double2 *>(g.X + (long long)dst * CS);
+#pragma unroll
+                    for (int i = 0; i < P / 2; ++i) xq[i] = make_double2(xv[2 * i], xv[2 * i + 1]);
+                }
+                running += tot;
+                if constexpr (NW > 1) __syncthreads();
+            }
+            bsync<NW>();
+            n0 = running;
+        }
+        if (exit_code == -1) {
+            // nothing: reported through the counters
+        } else if (n0 < a.min_hi) {
+            exit_code = DN_EXIT_FEW_HICOV;                               // nmf.py:232-233
+        } else {
+            g.n0 = g.n_cur = n0;
+            g.cs = n0; g.nb0 = 1; g.nalive = 1;
+            {   // rs(F_start)
+                double rs[P];
+#pragma unroll
+                for (int i = 0; i < P; ++i) rs[i] = 0.0;
+                for (int col = tid; col < n0; col += NT) {
+                    double x[P];
+                    load_col<P>(g.X + col * CS, x);
+#pragma unroll
+                    for (int i = 0; i < P; ++i) rs[i] += x[i];
+                }
+                block_sum_vec<P, NW>(rs, g.gpart, g.rs0);
+            }
+            bool any_empty = false;
+            for (int i = 0; i < p; ++i) any_empty |= !(g.rs0[i] > 0.0);
+            if (any_empty) {
+                exit_code = DN_EXIT_EMPTY_SAMPLE;                        // nmf.py:241-242
+            } else {
+                const bool store_e = (a.e_first != nullptr) && (n0 == L);
+                // (4) first fit (nmf.py:245-254), then the bin-drop loop (nmf.py:273-324); one nmf() call site
+                bool first = true, in_loop = false;
+                double rmax = 0.0;
+                for (;;) {
+                    run_nmf_small<P, NW>(a, g, first, true, (first && store_e) ? a.e_first + o0 : nullptr);
+                    nmf_calls += 1; sum_cols += g.n_cur;
+                    if (first) {
+                        if (tid < P) {
+                            g.rho[tid] = 1.0 - g.rs0[tid] / (g.tmp[tid] + 1.0);
+                            g.K0[tid] = g.K[tid];
+                            g.rsC0[tid] = g.rsC[tid];
+                        }
+                        bsync<NW>();
+                        if (median_one_minus(g.rho, p) > 1.0) {
+                            exit_code = DN_EXIT_MEDIAN;                  // nmf.py:257-258
+                            break;
+                        }
+                        double rmin = g.rho[0];
+                        rmax = g.rho[0];
+                        for (int i = 1; i < p; ++i) { rmin = fmin(rmin, g.rho[i]); rmax = fmax(rmax, g.rho[i]); }
+                        if (!(n0 >= a.min_len && rmin <= 0.2 && !a.skip)) {      // nmf.py:265
+                            exit_code = DN_EXIT_NO_SELECTION;
+                            break;
+                        }
+                        g.cs = (n0 + a.bins - 1) / a.bins;               // utils.py:176-192
+                        g.nb0 = (n0 + g.cs - 1) / g.cs;
+                        g.nalive = g.nb0;
+                        if (tid < g.nb0) g.alive[tid] = tid;
+                        if (NT < DN_MAX_BINS && tid + NT < g.nb0) g.alive[tid + NT] = tid + NT;
+                        bsync<NW>();
+                        in_loop = true;
+                        first = false;
+                    } else {
+                        double mn = g.tmp[0];
+                        for (int i = 1; i < p; ++i) mn = fmin(mn, g.tmp[i]);
+                        if (mn == 0.0) break;                            // nmf.py:315-316
+                        bsync<NW>();
+                        if (tid < P) g.rho[tid] = 1.0 - g.rsF[tid] / (g.rsC[tid] + 1.0);   // nmf.py:318-321
+                        bsync<NW>();
+                        rmax = g.rho[0];
+                        for (int i = 1; i < p; ++i) rmax = fmax(rmax, g.rho[i]);
+                        if (g.nalive <= a.min_bins || g.n_cur < a.min_len) break;        // nmf.py:323
+                    }
+                    if (!(rmax > 0.1)) break;                            // nmf.py:273
+                    ran = 1;
+                    // mean squared-relative-residual per alive bin (nmf.py:280-283); one warp per bin.
+                    // Alive bins are contiguous: bin k of the current matrix starts at column k * cs.
+                    for (int k = warp; k < g.nalive; k += NW) {
+                        const int b = g.alive[k];
+                        const int wdt = min(g.cs, g.n0 - b * g.cs);
+                        const double *rr = g.resb + k * g.cs;
+                        double s = 0.0;
+                        for (int j = lane; j < wdt; j += 32) s += rr[j];
+                        s = warp_sum(s);
+                        if (lane == 0) g.binm[k] = s / (double)wdt;
+                    }
+                    bsync<NW>();
+                    int kd = 0;
+                    double best = g.binm[0];
+                    for (int k = 1; k < g.nalive; ++k)
+                        if (g.binm[k] > best) { best = g.binm[k]; kd = k; }
+                    if (best == 0.0) break;                              // nmf.py:286-287
+                    const int bd = g.alive[kd];
+                    const int wd = min(g.cs, g.n0 - bd * g.cs);
+                    bsync<NW>();
+                    if (tid == 0)
+                        for (int k = kd; k < g.nalive - 1; ++k) g.alive[k] = g.alive[k + 1];
+                    {   // rotate the dropped bin's columns to the end of the current matrix (M is scratch)
+                        const int a0 = kd * g.cs;
+                        const int tail = g.n_cur - a0 - wd;
+                        const double2 *xs = reinterpret_cast<const double2 *>(g.X + (long long)a0 * CS);
+                        double2 *ms = reinterpret_cast<double2 *>(g.M + (long long)a0 * CS);
+                        const int h = CS / 2;
+                        for (int e = tid; e < (tail + wd) * h; e += NT) ms[e] = xs[e];
+                        bsync<NW>();
+                        double2 *xd = reinterpret_cast<double2 *>(g.X + (long long)a0 * CS);
+                        for (int e = tid; e < tail * h; e += NT) xd[e] = ms[wd * h + e];
+                        for (int e = tid; e < wd * h; e += NT) xd[tail * h + e] = ms[e];
+                    }
+                    bsync<NW>();
+                    g.nalive -= 1;
+                    g.n_cur -= wd;
+                    drops |= 1ull << bd;
+                    if (g.n_cur < 2) break;                              // svds ValueError swallowed, nmf.py:306-310
+                }
+                if (in_loop) {
+                    bsync<NW>();
+                    bool fallback = true;
+                    exit_code = DN_EXIT_FALLBACK;
+                    if (rmax < 0.2) {                                    // nmf.py:327-346
+                        floor_abs(g.K, g.K, p);
+                        double s = 0.0;
+                        for (int j = tid; j < n0; j += NT) {
+                            double x[P];
+                            load_col<P>(g.X + j * CS, x);
+                            double e = -1.0e300;
+#pragma unroll
+                            for (int i = 0; i < P; ++i)
+                                if (i < p) e = fmax(e, x[i] / g.K[i]);
+                            s += e;
+                        }
+                        const double S = block_sum<NT>(s, g.red);
+                        if (tid < P) g.rho[tid] = 1.0 - g.rs0[tid] / (g.K[tid] * S + 1.0);
+                        __syncthreads();
+                        rmax = g.rho[0];
+                        for (int i = 1; i < p; ++i) rmax = fmax(rmax, g.rho[i]);
+                        if (rmax > 0.9) {
+                            exit_code = DN_EXIT_FALLBACK_HIGH;
+                        } else {
+                            exit_code = DN_EXIT_REFINED;
+                            fallback = false;
+                            k_is_refined = true;
+                        }
+                    }
+                    if (fallback) {                                      // nmf.py:342-353
+                        __syncthreads();
+                        if (tid < P) g.rho[tid] = 1.0 - g.rs0[tid] / (g.rsC0[tid] + 1.0);
+                        __syncthreads();
+                    }
+                }
+            }
+        }
+        // (5) outputs
+        __syncthreads();
+        const bool is_default = exit_code == DN_EXIT_FEW_HICOV || exit_code == DN_EXIT_EMPTY_SAMPLE ||
+                                exit_code == DN_EXIT_MEDIAN || exit_code == -1;
+        if (!is_default && !k_is_refined) {
+            // K of the first fit; floored unless the estimate keeps the fit's own columns (n0 == L)
+            if (n0 == L) {
+                if (tid < P) g.K[tid] = g.K0[tid];
+                __syncthreads();
+            } else {
+                floor_abs(g.K0, g.K, p);
+            }
+        }
+        if (tid < p) {
+            double r = is_default ? 0.0 : g.rho[tid];
+            r = r > 0.9 ? 0.9 : r;                                       // nmf.py:398-399
+            r = r < 0.0 ? 0.0 : r;
+            a.rho[(long long)gid * p + tid] = r;
+            if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
+        }
+        if (tid == 0) {
+            a.ran[gid] = (unsigned char)(is_default ? 0 : ran);
+            if (cnt) {
+                cnt[DN_CNT_EXIT] = exit_code; cnt[DN_CNT_N_HICOV] = n0; cnt[DN_CNT_NMF_CALLS] = nmf_calls;
+                cnt[DN_CNT_SUM_COLS] = sum_cols; cnt[DN_CNT_EIG_STEPS] = g.eig_steps;
+                cnt[DN_CNT_DROPS_LO] = (int)(drops & 0xffffffffull); cnt[DN_CNT_DROPS_HI] = (int)(drops >> 32);
+                cnt[DN_CNT_RESIDENT] = (int)RES | (g.eig_fallbacks << 1);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int P, int NW, bool RES>
+int launch_small_one(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+    auto kern = nmfoa_small_kernel<P, NW, RES>;
+    DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+    kern<<<plan->ctas, NW * 32, plan->smem_bytes, st>>>(a);
+    DN_CUDA(cudaGetLastError());
+    return DN_OK;
+}
+
+template <int P>
+int launch_small(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+    if (plan->resident_cols > 0) {
+        switch (plan->threads) {
+            case 32: return launch_small_one<P, 1, true>(a, plan, st);
+            case 64: return launch_small_one<P, 2, true>(a, plan, st);
+            case 128: return launch_small_one<P, 4, true>(a, plan, st);
+            case 256: return launch_small_one<P, 8, true>(a, plan, st);
+            case 512: return launch_small_one<P, 16, true>(a, plan, st);
+        }
+        return dn_fail(DN_ERR_INVALID, "plan.threads must be 32..512 (power of two) on the small-p path%s");
+    }
+    if (plan->threads != 256) return dn_fail(DN_ERR_INVALID, "streamed small-p plans use 256 threads%s");
+    return launch_small_one<P, 8, false>(a, plan, st);
+}
+
+}  // namespace

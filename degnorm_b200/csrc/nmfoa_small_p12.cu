@@ -1,0 +1,4 @@
+// degnorm_b200 -- small-p fused baseline-selection kernels, P = 12 instantiation (see nmfoa_small.cuh).
+#include "nmfoa_small.cuh"
+
+int dn_launch_small12(const KArgs &a, const dn_plan *plan, cudaStream_t st) { return launch_small<12>(a, plan, st); }

@@ -1,0 +1,4 @@
+// degnorm_b200 -- small-p fused baseline-selection kernels, P = 8 instantiation (see nmfoa_small.cuh).
+#include "nmfoa_small.cuh"
+
+int dn_launch_small8(const KArgs &a, const dn_plan *plan, cudaStream_t st) { return launch_small<8>(a, plan, st); }

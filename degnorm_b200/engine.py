@@ -15,7 +15,10 @@ import torch
 from . import _lib
 from ._lib import DnParams, DnPlan, check
 
+# resident tiers (columns) of the tiled kernel (p > 12)
 RESIDENT_TIERS = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
+# small-p kernel (p <= 12): (columns, warps per CTA); the column caps make whole numbers of CTAs fill an SM's 227 KB
+SMALL_TIERS = ((32, 1), (64, 1), (96, 1), (136, 2), (208, 2), (288, 4), (448, 4), (920, 8))
 
 
 class Params(object):
@@ -69,12 +72,14 @@ class _Bucket(object):
 class ShardEngine(object):
     """One GPU's shard.  load() takes device tensors; run() leaves device tensors in self.out."""
 
-    def __init__(self, prm, p, device, group=None, force_streamed=False):
+    def __init__(self, prm, p, device, group=None, force_streamed=False, small_tiers=None, use_row_max=True):
         self.prm = prm
         self.p = int(p)
         self.device = torch.device(device)
         self.group = group
         self.force_streamed = force_streamed
+        self.small_tiers = small_tiers
+        self.use_row_max = use_row_max
         self.cprm = prm.to_c(p)
         with torch.cuda.device(self.device):
             self.sm_count, self.max_smem, self.cc = _lib.device_info()
@@ -98,18 +103,18 @@ class ShardEngine(object):
         self.reads = reads.contiguous()
         self._plan()
 
-    def _make_plan(self, max_cols, n_work, want_resident, for_init=False):
+    def _make_plan(self, max_cols, n_work, want_resident, for_init=False, warps=0):
         plan = DnPlan()
         check(self.lib.dn_make_plan(C.byref(self.cprm), int(max_cols), int(n_work), int(want_resident),
-                                    int(for_init), self.sm_count, self.max_smem, C.byref(plan)))
+                                    int(for_init), int(warps), self.sm_count, self.max_smem, C.byref(plan)))
         return plan
 
-    def _bucket(self, ids, cand, want_resident, for_init=False):
+    def _bucket(self, ids, cand, want_resident, for_init=False, warps=0):
         b = _Bucket()
         order = ids[np.argsort(-cand[ids], kind="stable")]
         b.n = len(order)
         b.max_cols = int(cand[ids].max())
-        b.plan = self._make_plan(b.max_cols, b.n, want_resident, for_init)
+        b.plan = self._make_plan(b.max_cols, b.n, want_resident, for_init, warps)
         b.order = torch.from_numpy(order.astype(np.int32)).to(self.device)
         b.ws = torch.empty(int(b.plan.ws_bytes), dtype=torch.uint8, device=self.device)
         b.stream = torch.cuda.Stream(device=self.device)
@@ -130,6 +135,21 @@ class ShardEngine(object):
             return
         left = np.ones(n, dtype=bool)
         prev = 0
+        if self.p <= 12:
+            tiers = self.small_tiers if self.small_tiers is not None else SMALL_TIERS
+            for tier, warps in tiers:
+                sel = np.flatnonzero(left & (cand <= tier) & (cand > prev))
+                if len(sel):
+                    b = self._bucket(sel, cand, tier, warps=warps)
+                    if b.plan.resident_cols == 0:
+                        raise RuntimeError("small-p tier %d does not fit in shared memory" % tier)
+                    self.buckets.append(b)
+                    left[sel] = False
+                prev = tier
+            rest = np.flatnonzero(left)
+            if len(rest):
+                self.buckets.append(self._bucket(rest, cand, 0))
+            return
         for tier in RESIDENT_TIERS:
             plan = self._make_plan(tier, 1, tier)
             if plan.resident_cols < tier:
@@ -169,6 +189,7 @@ class ShardEngine(object):
         init_counters = torch.zeros((nn, _lib.DN_NCOUNTERS), dtype=torch.int32, device=dev)
         sums_ws = torch.empty(int(lib.dn_sums_workspace_bytes(nn, p)), dtype=torch.uint8, device=dev)
         kfac = torch.zeros((nn, p), **f64)
+        row_max = torch.zeros((nn, p), **f64) if self.use_row_max else None
         want_e_first = want_estimates and prm.downsample_rate == 1 and n > 0
         e_first = torch.zeros(int(self.offsets_np[-1]), **f64) if want_e_first else None
         ds_dev = torch.from_numpy(np.ascontiguousarray(ds_offsets, dtype=np.int32)).to(dev) if ds_offsets is not None else None
@@ -186,7 +207,7 @@ class ShardEngine(object):
         if n > 0:
             b = self.init_bucket
             check(lib.dn_init_ratio_svd(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm),
-                                        C.byref(b.plan), _ptr(est_rs), _ptr(cov_rs), _ptr(init_counters), _ptr(b.ws),
+                                        C.byref(b.plan), _ptr(est_rs), _ptr(cov_rs), _ptr(row_max), _ptr(init_counters), _ptr(b.ws),
                                         b.ws.numel(), C.c_void_p(main.cuda_stream)))
             check(lib.dn_init_sums(_ptr(est_rs), _ptr(cov_rs), _ptr(self.reads), n, p, _ptr(rho0), _ptr(sums),
                                    _ptr(sums_ws), sums_ws.numel(), C.c_void_p(main.cuda_stream)))
@@ -207,7 +228,7 @@ class ShardEngine(object):
                 b.stream.wait_stream(main)
                 check(lib.dn_baseline_selection(
                     _ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm), C.byref(b.plan),
-                    _ptr(scale), _ptr(ds_dev[it]) if ds_dev is not None else C.c_void_p(0),
+                    _ptr(scale), _ptr(ds_dev[it]) if ds_dev is not None else C.c_void_p(0), _ptr(row_max),
                     _ptr(rho), _ptr(ran[it]), _ptr(counters[it]), _ptr(kfac),
                     _ptr(e_first) if (last and e_first is not None) else C.c_void_p(0),
                     _ptr(b.ws), b.ws.numel(), C.c_void_p(b.stream.cuda_stream)))

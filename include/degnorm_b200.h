@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 1
+#define DN_ABI_VERSION 2
 #define DN_MAX_BINS 64      /* baseline-selection bins held in the fused kernel (reference default: 20) */
 #define DN_MAX_SAMPLES 128  /* p supported by the fused kernels in this round */
 #define DN_NCOUNTERS 8      /* int32 counters per gene, see dn_counter */
@@ -80,7 +80,7 @@ typedef struct dn_params {
 
 /* Launch plan for one bucket of genes (all genes of one launch share a shared-memory carve-up). */
 typedef struct dn_plan {
-    int32_t tile;           /* Gram tile edge per thread: 2, 4 or 8                             */
+    int32_t tile;           /* 0: small-p kernel (p <= 12); 4 or 8: Gram tile edge of the tiled kernel */
     int32_t threads;        /* CTA size                                                         */
     int32_t ctas;           /* persistent CTAs to launch                                        */
     int32_t resident_cols;  /* columns of x and lambda held in shared memory (0: none)          */
@@ -100,28 +100,34 @@ int dn_device_info(int32_t *sm_count, int32_t *max_smem_optin, int32_t *cc);
 /* Fill `plan` for a bucket whose largest gene has max_cols candidate columns (L for the init pass and
  * for downsample_rate 1, ceil(L/rate) otherwise).  want_resident: shared-memory column capacity wanted
  * (0 forces the streamed path, -1 = as many as fit).  for_init=1 sizes the workspace for dn_init_ratio_svd.
+ * warps: warps per CTA on the small-p path (1, 2, 4, 8, 16; 0 = chosen from the tier), ignored elsewhere.
+ * On the small-p path (p <= 12, for_init = 0) a bucket is wholly resident (max_cols fit in shared memory) or
+ * wholly streamed; on the tiled path residency is decided per gene.
  * Pure host arithmetic (no device call): sm_count / max_smem come from dn_device_info. */
 int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t want_resident, int32_t for_init,
-                 int32_t sm_count, int32_t max_smem_optin, dn_plan *plan);
+                 int32_t warps, int32_t sm_count, int32_t max_smem_optin, dn_plan *plan);
 
 /* Replaces run_ratio_svd_serial / ratio_svd over all genes + the two row sums run() takes of it
  * (nmf.py:109-140, 521-527): est_rowsum[g,i] = sum_j max(R1(F_g)_ij, F_g[i,j]), cov_rowsum[g,i] = sum_j F_g[i,j]
- * on the raw, unscaled, unfiltered matrices. */
+ * on the raw, unscaled, unfiltered matrices.  row_max (n x p or NULL): row_max[g,i] = max_j F_g[i,j], which
+ * dn_baseline_selection can take instead of re-scanning every gene for the 0.1*max(F) threshold (nmf.py:76):
+ * max_j(F_ij / s_i) = (max_j F_ij) / s_i exactly, because division by a positive scale is monotone. */
 int dn_init_ratio_svd(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
                       const dn_params *prm, const dn_plan *plan,
-                      double *est_rowsum, double *cov_rowsum, int32_t *counters,
+                      double *est_rowsum, double *cov_rowsum, double *row_max, int32_t *counters,
                       void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Replaces adjust_coverage_curves + par_apply_baseline_selection + baseline_selection + nmf +
  * rank_one_approx + get_high_coverage_idx + shift_bins + downsample_2d for one outer iteration
  * (nmf.py:55-107, 142-146, 160-406).  scale = current scale factors (p, device; coverage is divided by
  * them on load).  ds_start = systematic-sample offset per gene id (NULL when downsample_rate == 1).
+ * row_max = row maxima from dn_init_ratio_svd (NULL: every gene is scanned for its maximum).
  * Outputs: rho (n x p, already clipped to [0, 0.9] as nmf.py:398-399), ran (n, uint8),
  * counters (n x DN_NCOUNTERS), kfac (n x p: |K| floored as nmf.py:361-362, input of dn_estimates),
  * e_first (sum_g L_g doubles or NULL: E of the first fit for genes where no column was filtered). */
 int dn_baseline_selection(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
                           const dn_params *prm, const dn_plan *plan,
-                          const double *scale, const int32_t *ds_start,
+                          const double *scale, const int32_t *ds_start, const double *row_max,
                           double *rho, uint8_t *ran, int32_t *counters, double *kfac, double *e_first,
                           void *workspace, int64_t workspace_bytes, void *stream);
 
