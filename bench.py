@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-genes", type=int, default=0, help="genes in the CPU sample (default: 2 per core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tiers", default="", help="small-p tiers as cols:warps,... (tuning)")
     return ap.parse_args()
 
 
@@ -228,7 +229,8 @@ def main():
     reads = torch.clamp(reads, min=1.0)
     prm = Params(**kw)
     ds = draw_offsets(n, prm)
-    eng = ShardEngine(prm, p, dev, group=group)
+    tiers = tuple(tuple(int(x) for x in t.split(":")) for t in args.tiers.split(",")) if args.tiers else None
+    eng = ShardEngine(prm, p, dev, group=group, small_tiers=tiers)
     eng.load(cov, off, reads)
     eng.record_events = True
 

@@ -73,9 +73,9 @@ __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_co
     c.binm = o;  o += DN_MAX_BINS;
     c.alive = o; o += DN_MAX_BINS / 2;
     c.ibuf = o;  o += 16;
-    c.G = o;     o += (long long)P * P;
+    c.G = o;     o += (long long)nw * P * P;                 // one copy per warp
     c.vx = o;    o += (long long)nw * 2 * P;
-    c.gpart = o; o += (long long)nw * SMALL_GPART;
+    c.gpart = o; o += (long long)(nw > 1 ? 2 : 1) * nw * SMALL_GPART;   // two alternating partial-sum buffers
     c.tab = o;   o += 32;                       // 16 tiles x 4 ints
     const long long cs = small_cs(P);
     c.X = o;     o += resident_cols > 0 ? cs * resident_cols : 0;

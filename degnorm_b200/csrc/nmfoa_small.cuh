@@ -44,7 +44,7 @@ struct SGene {
     int *alive, *ibuf, *tab;
     double *X, *M, *resb, *tb;
     int n0, n_cur, cs, nb0, nalive;
-    int eig_steps, eig_fallbacks;
+    int eig_steps, eig_fallbacks, gpar;
     double *B0;
     int r0, offA, offB, ks, u0, u1, u2;     // this lane's Gram tile
     bool tile_ok;
@@ -98,6 +98,7 @@ __device__ __forceinline__ void block_sum_vec(double (&x)[NV], double *part, dou
         }
         __syncwarp();
     } else {
+        __syncthreads();          // `part` doubles as the Gram partial-sum buffer: every warp must be done reading it
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < NV; ++k) part[warp * NV + k] = x[k];
@@ -194,26 +195,31 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
         }
         __syncwarp();
     } else {
+        // one barrier per pass: partials go to one of two alternating buffers, then every warp sums all of them
+        // (same order everywhere) into its own copy of G
+        double *gp = g.gpart + (long long)g.gpar * (NW * SMALL_GPART);
+        g.gpar ^= 1;
         if (g.ks == 0 && g.tile_ok) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int q = 0; q < TC; ++q) g.gpart[warp * SMALL_GPART + lane * (2 * TC) + r * TC + q] = acc[r][q];
+                for (int q = 0; q < TC; ++q) gp[warp * SMALL_GPART + lane * (2 * TC) + r * TC + q] = acc[r][q];
         }
         __syncthreads();
-        for (int e = tid; e < NTILE * 2 * TC; e += NT) {
+        double *Gw = g.G + warp * (P * P);
+        for (int e = lane; e < NTILE * 2 * TC; e += 32) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s += g.gpart[w * SMALL_GPART + e];
+            for (int w = 0; w < NW; ++w) s += gp[w * SMALL_GPART + e];
             const int t = e / (2 * TC), rq = e - t * (2 * TC);
             const int r = rq / TC, q = rq - r * TC;
             const int i = g.tab[t * 4] + r, j = g.tab[t * 4 + 1 + q];
             if (i <= j) {
-                g.G[i * P + j] = s;
-                g.G[j * P + i] = s;
+                Gw[i * P + j] = s;
+                Gw[j * P + i] = s;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -226,8 +232,9 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *vx = g.vx + warp * (2 * P);
     const int row = lane % P;
+    const double *Gw = g.G + (NW > 1 ? warp * (P * P) : 0);
     double grow[P];
-    load_col<P>(g.G + row * P, grow);
+    load_col<P>(Gw + row * P, grow);
     int par = 0;
     // y = scale * G v, exchanged through the warp-private buffer (double-buffered: one __syncwarp per step)
     auto step = [&](double scale) {
@@ -277,36 +284,43 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
             break;
         }
         const double inv = rsqrt(n2);
-        d = 0.0;
+        // d = max_k |v_k - old_k|, tracked on the high words (|x| as an integer orders like |x|): ~2^-20 relative
+        // resolution, which is plenty for a stopping test
+        int hd = 0;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
             v[k] *= inv;
-            d = fmax(d, fabs(v[k] - old[k]));
+            hd = max(hd, __double2hiint(v[k] - old[k]) & 0x7fffffff);
         }
+        d = __hiloint2double(hd, 0);
         inv_lam = inv;
-        if (d <= EIG_TOL) { ok = 1; break; }
+        if (d < EIG_TOL) { ok = 1; break; }
         if (checked >= 2 && steps >= 8 && d > 0.75 * prev) break;     // small spectral gap: squaring solver
         prev = d;
     }
     if (ok == 1) {
-        // warm-start distrust rule (see nmfoa_tiled.cu eig_warp): an entry ~0 on a sample that has coverage
-        double vmin = 1.0e300, vmax = 0.0;
+        // warm-start distrust rule (see nmfoa_tiled.cu eig_warp): an entry ~0 on a sample that has coverage.
+        // v >= 0, so high words order like the values; a ratio below 1e-3 needs exponents >= 9 apart.
+        int hmin = 0x7fffffff, hmax = 0;
 #pragma unroll
         for (int k = 0; k < P; ++k) {
-            if (k < a.p) vmin = fmin(vmin, v[k]);
-            vmax = fmax(vmax, v[k]);
+            const int h = __double2hiint(v[k]);
+            hmax = max(hmax, h);
+            hmin = min(hmin, k < a.p ? h : 0x7fffffff);
         }
-        if (vmin < EIG_SUSPECT * vmax) {
-            vmin = 1.0e300;
+        if (hmax - hmin >= (8 << 20)) {
+            double vmin = 1.0e300, vmax = 0.0;
 #pragma unroll
-            for (int k = 0; k < P; ++k)
-                if (k < a.p && g.G[k * P + k] > 0.0) vmin = fmin(vmin, v[k]);
+            for (int k = 0; k < P; ++k) {
+                vmax = fmax(vmax, v[k]);
+                if (k < a.p && Gw[k * P + k] > 0.0) vmin = fmin(vmin, v[k]);
+            }
             if (vmin < EIG_SUSPECT * vmax) ok = 2;
         }
     }
     g.eig_steps += steps;
     if (ok == 1) {
-        if (checked == 1 && d <= 0.02 * EIG_TOL) hint = steps > 1 ? steps - 1 : 1;
+        if (checked == 1 && d < 0.02 * EIG_TOL) hint = steps > 1 ? steps - 1 : 1;
         else hint = steps;
     } else {                                       // uniform across the CTA (every warp solved the same matrix)
         if constexpr (NW > 1) __syncthreads();
@@ -449,6 +463,7 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) nmfoa_small_kernel(const KAr
     for (int e = tid; e < N_SMALL * P; e += NT) sm[e] = 0.0;
     g.eig_steps = 0;
     g.eig_fallbacks = 0;
+    g.gpar = 0;
     __syncthreads();
 
     for (;;) {
