@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-genes", type=int, default=0, help="genes in the CPU sample (default: 2 per core)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--serial-buckets", action="store_true", help="tuning: run the tiers one after another")
     ap.add_argument("--tiers", default="", help="small-p tiers as cols:warps,... (tuning)")
     return ap.parse_args()
 
@@ -233,6 +234,7 @@ def main():
     eng = ShardEngine(prm, p, dev, group=group, small_tiers=tiers)
     eng.load(cov, off, reads)
     eng.record_events = True
+    eng.serial_buckets = args.serial_buckets
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -291,6 +293,13 @@ def main():
                     note="algorithmic = as-if-streamed bytes; resident genes never touch HBM again, so frac > 1 is possible",
                     resident_fraction=float((cnt[-1, :, 7] & 1).mean()),
                     nmf_calls_per_gene=float(cnt[:, :, 2].mean()), phases_ms_per_step={k: v / args.steps for k, v in all_ms.items()})
+    bk = eng.bucket_ms()
+    cnt_last = cnt[-1]
+    roofline["buckets"] = [dict(max_cols=bb.max_cols, genes=bb.n, threads=int(bb.plan.threads), ctas=int(bb.plan.ctas),
+                                smem=int(bb.plan.smem_bytes), resident=int(bb.plan.resident_cols),
+                                end_ms=[round(bk[it][k], 2) for it in sorted(bk)],
+                                sum_cols=int(cnt_last[bb.order.cpu().numpy(), 3].sum()))
+                           for k, bb in enumerate(eng.buckets)]
     clock_summary = None
     if rank == 0:
         clocks.stop_flag = True

@@ -46,8 +46,7 @@ struct SGene {
     int n0, n_cur, cs, nb0, nalive;
     int eig_steps, eig_fallbacks, gpar;
     double *B0;
-    int r0, offA, offB, ks, u0, u1, u2;     // this lane's Gram tile
-    bool tile_ok;
+    int tpack;      // this lane's Gram tile: r0 | offA << 4 | offB << 8 | u0 << 12 | u1 << 16 | u2 << 20; -1: none
 };
 
 template <int P>
@@ -141,10 +140,9 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
 #pragma unroll
                 for (int i = 0; i < P; ++i) {
                     const double res = fma(v[i], t, -x[i]);        // est - x
-                    double lam = m[i] - x[i];
-                    lam = fma(-c, res, lam);
-                    lam = lam < 0.0 ? 0.0 : lam;
-                    m[i] = x[i] + lam;
+                    const double w = fma(-c, res, m[i] - x[i]);    // lambda - c (est - x)
+                    // x + max(0, w), branch- and select-free: w + |w| = 2 max(0, w) exactly, the fma rounds once
+                    m[i] = fma(0.5, w + fabs(w), x[i]);
                 }
                 double2 *mq = reinterpret_cast<double2 *>(g.M + col * CS);
 #pragma unroll
@@ -152,19 +150,21 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
             }
             __syncwarp();
         }
-        if (g.tile_ok) {
+        if (g.tpack >= 0) {
             const int cend = min(b0 + 32, n);
-            const double *mc = g.M + (b0 + g.ks) * CS;
+            const int ks = lane / NTP;
+            const int oR = g.tpack & 15, oA = (g.tpack >> 4) & 15, oB = (g.tpack >> 8) & 15;
+            const double *mc = g.M + (b0 + ks) * CS;
 #pragma unroll 4
-            for (int col = b0 + g.ks; col < cend; col += KS, mc += KS * CS) {
-                const double2 ar = *reinterpret_cast<const double2 *>(mc + g.r0);
-                const double2 ua = *reinterpret_cast<const double2 *>(mc + g.offA);
+            for (int col = b0 + ks; col < cend; col += KS, mc += KS * CS) {
+                const double2 ar = *reinterpret_cast<const double2 *>(mc + oR);
+                const double2 ua = *reinterpret_cast<const double2 *>(mc + oA);
                 acc[0][0] = fma(ar.x, ua.x, acc[0][0]);
                 acc[0][1] = fma(ar.x, ua.y, acc[0][1]);
                 acc[1][0] = fma(ar.y, ua.x, acc[1][0]);
                 acc[1][1] = fma(ar.y, ua.y, acc[1][1]);
                 if constexpr (TC == 3) {
-                    const double ub = mc[g.offB];
+                    const double ub = mc[oB];
                     acc[0][2] = fma(ar.x, ub, acc[0][2]);
                     acc[1][2] = fma(ar.y, ub, acc[1][2]);
                 }
@@ -180,13 +180,13 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
             for (int q = 0; q < TC; ++q) acc[r][q] += __shfl_xor_sync(0xffffffffu, acc[r][q], o);
 
     if constexpr (NW == 1) {
-        if (g.ks == 0 && g.tile_ok) {
-            const int uu[3] = {g.u0, g.u1, g.u2};
+        if (lane < NTP && g.tpack >= 0) {
+            const int uu[3] = {(g.tpack >> 12) & 15, (g.tpack >> 16) & 15, (g.tpack >> 20) & 15};
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
                 for (int q = 0; q < TC; ++q) {
-                    const int i = g.r0 + r, j = uu[q];
+                    const int i = (g.tpack & 15) + r, j = uu[q];
                     if (i <= j) {
                         g.G[i * P + j] = acc[r][q];
                         g.G[j * P + i] = acc[r][q];
@@ -199,7 +199,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
         // (same order everywhere) into its own copy of G
         double *gp = g.gpart + (long long)g.gpar * (NW * SMALL_GPART);
         g.gpar ^= 1;
-        if (g.ks == 0 && g.tile_ok) {
+        if (lane < NTP && g.tpack >= 0) {
 #pragma unroll
             for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -448,16 +448,15 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) nmfoa_small_kernel(const KAr
     }
     {   // this lane's Gram tile; table of all tiles for the cross-warp sum
         const int t = lane % Cfg::NTP;
-        g.ks = lane / Cfg::NTP;
-        int r0, c0;
+        int r0, c0, offA, offB, u0, u1, u2;
         bool ok;
         tile_of<P>(t, r0, c0, ok);
-        g.tile_ok = ok;
-        g.r0 = r0;
-        if (TC == 3 && ((c0 / 3) & 1)) { g.offA = c0 + 1; g.offB = c0; g.u0 = c0 + 1; g.u1 = c0 + 2; g.u2 = c0; }
-        else { g.offA = c0; g.offB = c0 + 2; g.u0 = c0; g.u1 = c0 + 1; g.u2 = c0 + 2; }
+        if (TC == 3 && ((c0 / 3) & 1)) { offA = c0 + 1; offB = c0; u0 = c0 + 1; u1 = c0 + 2; u2 = c0; }
+        else { offA = c0; offB = c0 + 2; u0 = c0; u1 = c0 + 1; u2 = c0 + 2; }
+        if (TC == 2) { offB = 0; u2 = 0; }
+        g.tpack = ok ? (r0 | offA << 4 | offB << 8 | u0 << 12 | u1 << 16 | u2 << 20) : -1;
         if (tid < Cfg::NTP) {
-            g.tab[tid * 4] = g.r0; g.tab[tid * 4 + 1] = g.u0; g.tab[tid * 4 + 2] = g.u1; g.tab[tid * 4 + 3] = g.u2;
+            g.tab[tid * 4] = r0; g.tab[tid * 4 + 1] = u0; g.tab[tid * 4 + 2] = u1; g.tab[tid * 4 + 3] = u2;
         }
     }
     for (int e = tid; e < N_SMALL * P; e += NT) sm[e] = 0.0;

@@ -18,7 +18,7 @@ from ._lib import DnParams, DnPlan, check
 # resident tiers (columns) of the tiled kernel (p > 12)
 RESIDENT_TIERS = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
 # small-p kernel (p <= 12): (columns, warps per CTA); the column caps make whole numbers of CTAs fill an SM's 227 KB
-SMALL_TIERS = ((32, 1), (64, 1), (96, 1), (136, 2), (208, 2), (288, 4), (448, 4), (920, 8))
+SMALL_TIERS = ((36, 1), (64, 1), (96, 1), (154, 2), (204, 2), (284, 2), (420, 4), (856, 8))
 
 
 class Params(object):
@@ -79,6 +79,9 @@ class ShardEngine(object):
         self.group = group
         self.force_streamed = force_streamed
         self.small_tiers = small_tiers
+        self.serial_buckets = False
+        self.prioritise = True
+        self.bucket_starts = {}
         self.use_row_max = use_row_max
         self.cprm = prm.to_c(p)
         with torch.cuda.device(self.device):
@@ -117,10 +120,22 @@ class ShardEngine(object):
         b.plan = self._make_plan(b.max_cols, b.n, want_resident, for_init, warps)
         b.order = torch.from_numpy(order.astype(np.int32)).to(self.device)
         b.ws = torch.empty(int(b.plan.ws_bytes), dtype=torch.uint8, device=self.device)
-        b.stream = torch.cuda.Stream(device=self.device)
+        b.stream = None
         return b
 
     def _plan(self):
+        self._plan_buckets()
+        # Buckets run concurrently on their own streams.  The genes that take longest (most columns) must start
+        # first or they end up as the tail of the iteration: launch the largest-column bucket first and give it
+        # the highest stream priority, so its CTAs are placed before the many small ones fill the SMs.
+        self.buckets.sort(key=lambda b: -b.max_cols)
+        lo, hi = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -5)
+        for k, b in enumerate(self.buckets):
+            b.stream = torch.cuda.Stream(device=self.device, priority=max(hi, min(lo, hi + k)) if self.prioritise else 0)
+        if self.init_bucket is not None:
+            self.init_bucket.stream = torch.cuda.Stream(device=self.device)
+
+    def _plan_buckets(self):
         n, L, r = self.n, self.lengths, self.prm.downsample_rate
         self.buckets = []
         self.init_bucket = None
@@ -138,14 +153,13 @@ class ShardEngine(object):
         if self.p <= 12:
             tiers = self.small_tiers if self.small_tiers is not None else SMALL_TIERS
             for tier, warps in tiers:
+                while tier > prev and self._make_plan(tier, 1, tier, warps=warps).resident_cols == 0:
+                    tier -= 8                      # cap the tier at what fits beside this warp count's scratch
                 sel = np.flatnonzero(left & (cand <= tier) & (cand > prev))
                 if len(sel):
-                    b = self._bucket(sel, cand, tier, warps=warps)
-                    if b.plan.resident_cols == 0:
-                        raise RuntimeError("small-p tier %d does not fit in shared memory" % tier)
-                    self.buckets.append(b)
+                    self.buckets.append(self._bucket(sel, cand, tier, warps=warps))
                     left[sel] = False
-                prev = tier
+                prev = max(prev, tier)
             rest = np.flatnonzero(left)
             if len(rest):
                 self.buckets.append(self._bucket(rest, cand, 0))
@@ -195,6 +209,7 @@ class ShardEngine(object):
         ds_dev = torch.from_numpy(np.ascontiguousarray(ds_offsets, dtype=np.int32)).to(dev) if ds_offsets is not None else None
         self.launches = 0
         self.events = []
+        self.bucket_events = []
 
         def mark(name):
             if self.record_events:
@@ -224,7 +239,14 @@ class ShardEngine(object):
             last = it == n_iter - 1
             scale_used.copy_(scale)
             mark("pre_bs%d" % it)
-            for b in self.buckets:
+            for k, b in enumerate(self.buckets):
+                if self.serial_buckets:              # tuning aid: one bucket at a time, each timed on its own
+                    if k > 0:
+                        b.stream.wait_stream(self.buckets[k - 1].stream)
+                    if self.record_events:
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev0.record(b.stream if k > 0 else main)
+                        self.bucket_starts[(it, k)] = ev0
                 b.stream.wait_stream(main)
                 check(lib.dn_baseline_selection(
                     _ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm), C.byref(b.plan),
@@ -233,6 +255,10 @@ class ShardEngine(object):
                     _ptr(e_first) if (last and e_first is not None) else C.c_void_p(0),
                     _ptr(b.ws), b.ws.numel(), C.c_void_p(b.stream.cuda_stream)))
                 self.launches += 1
+                if self.record_events:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record(b.stream)
+                    self.bucket_events.append((it, k, ev))
             for b in self.buckets:
                 main.wait_stream(b.stream)
             mark("bs%d" % it)
@@ -267,6 +293,16 @@ class ShardEngine(object):
         out = {}
         for (n0, e0), (n1, e1) in zip(self.events[:-1], self.events[1:]):
             out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def bucket_ms(self):
+        """Per outer iteration, per bucket: ms from the start of the baseline-selection phase to the end of that
+        bucket's launch (buckets run concurrently on their own streams)."""
+        starts = {int(n[6:]): ev for n, ev in self.events if n.startswith("pre_bs")}
+        out = {}
+        for it, k, ev in self.bucket_events:
+            s = self.bucket_starts.get((it, k), starts[it])
+            out.setdefault(it, {})[k] = s.elapsed_time(ev)
         return out
 
     def bs_bytes_per_iteration(self):
