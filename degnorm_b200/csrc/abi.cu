@@ -316,7 +316,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         plan->smem_bytes = (int32_t)(small_carve(P, nw, (int)res).total * 8);
         plan->ws_cols = res > 0 ? 0 : (max_cols + 7) / 8 * 8;
         int per_sm = (int)((228ll * 1024) / (plan->smem_bytes + 1024));
-        if (per_sm > 16 / nw) per_sm = 16 / nw;                     // 128 registers per thread (__launch_bounds__)
+        if (per_sm > 12 / nw) per_sm = 12 / nw;                     // 168 registers per thread (__launch_bounds__)
         if (res == 0 && per_sm > 2) per_sm = 2;                      // streamed: keep the slabs in flight L2-sized
         if (per_sm < 1) per_sm = 1;
         long long ctas = (long long)sm_count * per_sm;

@@ -26,6 +26,10 @@
 
 namespace {
 
+// Stopping test of the eigen-solve: the last step moved no entry of v by more than this.  A step contracts the
+// error by lambda_2/lambda_1 (typically 0.05-0.2), so the vector returned is within ~1e-14 of the eigenvector.
+constexpr double SMALL_EIG_TOL = 1.0e-13;
+
 template <int P> struct SmallCfg;
 // TC: tile columns (tile = 2 rows x TC columns of G), NTILE tiles cover the upper triangle, NTP = tiles padded
 // to a power of two, KS = k-slices (lanes = NTP * KS)
@@ -129,45 +133,47 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
 #pragma unroll
         for (int q = 0; q < TC; ++q) acc[r][q] = 0.0;
 
-    for (int b0 = warp * 32; b0 < n; b0 += NT) {
-        if constexpr (UPDATE) {
-            const int col = b0 + lane;
-            if (col < n) {
-                double x[P], m[P];
-                load_col<P>(g.X + col * CS, x);
-                load_col<P>(g.M + col * CS, m);
-                const double t = dot_v<P>(v, m);
+    // this warp's contiguous column range (whole 32-column blocks)
+    const int per_warp = ((n + 31) / 32 + NW - 1) / NW * 32;
+    const int c_lo = min(warp * per_warp, n), c_hi = min(c_lo + per_warp, n);
+    if constexpr (UPDATE) {
+        // phase A: one lane per column; columns are independent, two in flight per lane
+#pragma unroll 2
+        for (int col = c_lo + lane; col < c_hi; col += 32) {
+            double x[P], m[P];
+            load_col<P>(g.X + col * CS, x);
+            load_col<P>(g.M + col * CS, m);
+            const double t = dot_v<P>(v, m);
 #pragma unroll
-                for (int i = 0; i < P; ++i) {
-                    const double res = fma(v[i], t, -x[i]);        // est - x
-                    const double w = fma(-c, res, m[i] - x[i]);    // lambda - c (est - x)
-                    // x + max(0, w), branch- and select-free: w + |w| = 2 max(0, w) exactly, the fma rounds once
-                    m[i] = fma(0.5, w + fabs(w), x[i]);
-                }
-                double2 *mq = reinterpret_cast<double2 *>(g.M + col * CS);
-#pragma unroll
-                for (int i = 0; i < P / 2; ++i) mq[i] = make_double2(m[2 * i], m[2 * i + 1]);
+            for (int i = 0; i < P; ++i) {
+                const double res = fma(v[i], t, -x[i]);        // est - x
+                const double w = fma(-c, res, m[i] - x[i]);    // lambda - c (est - x)
+                // x + max(0, w), branch- and select-free: w + |w| = 2 max(0, w) exactly, the fma rounds once
+                m[i] = fma(0.5, w + fabs(w), x[i]);
             }
-            __syncwarp();
+            double2 *mq = reinterpret_cast<double2 *>(g.M + col * CS);
+#pragma unroll
+            for (int i = 0; i < P / 2; ++i) mq[i] = make_double2(m[2 * i], m[2 * i + 1]);
         }
-        if (g.tpack >= 0) {
-            const int cend = min(b0 + 32, n);
-            const int ks = lane / NTP;
-            const int oR = g.tpack & 15, oA = (g.tpack >> 4) & 15, oB = (g.tpack >> 8) & 15;
-            const double *mc = g.M + (b0 + ks) * CS;
+        __syncwarp();
+    }
+    if (g.tpack >= 0) {
+        // phase B: this lane's Gram tile over its k-slice of the warp's columns
+        const int ks = lane / NTP;
+        const int oR = g.tpack & 15, oA = (g.tpack >> 4) & 15, oB = (g.tpack >> 8) & 15;
+        const double *mc = g.M + (c_lo + ks) * CS;
 #pragma unroll 4
-            for (int col = b0 + ks; col < cend; col += KS, mc += KS * CS) {
-                const double2 ar = *reinterpret_cast<const double2 *>(mc + oR);
-                const double2 ua = *reinterpret_cast<const double2 *>(mc + oA);
-                acc[0][0] = fma(ar.x, ua.x, acc[0][0]);
-                acc[0][1] = fma(ar.x, ua.y, acc[0][1]);
-                acc[1][0] = fma(ar.y, ua.x, acc[1][0]);
-                acc[1][1] = fma(ar.y, ua.y, acc[1][1]);
-                if constexpr (TC == 3) {
-                    const double ub = mc[oB];
-                    acc[0][2] = fma(ar.x, ub, acc[0][2]);
-                    acc[1][2] = fma(ar.y, ub, acc[1][2]);
-                }
+        for (int col = c_lo + ks; col < c_hi; col += KS, mc += KS * CS) {
+            const double2 ar = *reinterpret_cast<const double2 *>(mc + oR);
+            const double2 ua = *reinterpret_cast<const double2 *>(mc + oA);
+            acc[0][0] = fma(ar.x, ua.x, acc[0][0]);
+            acc[0][1] = fma(ar.x, ua.y, acc[0][1]);
+            acc[1][0] = fma(ar.y, ua.x, acc[1][0]);
+            acc[1][1] = fma(ar.y, ua.y, acc[1][1]);
+            if constexpr (TC == 3) {
+                const double ub = mc[oB];
+                acc[0][2] = fma(ar.x, ub, acc[0][2]);
+                acc[1][2] = fma(ar.y, ub, acc[1][2]);
             }
         }
     }
@@ -294,7 +300,7 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
         }
         d = __hiloint2double(hd, 0);
         inv_lam = inv;
-        if (d < EIG_TOL) { ok = 1; break; }
+        if (d < SMALL_EIG_TOL) { ok = 1; break; }
         if (checked >= 2 && steps >= 8 && d > 0.75 * prev) break;     // small spectral gap: squaring solver
         prev = d;
     }
@@ -320,7 +326,7 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
     }
     g.eig_steps += steps;
     if (ok == 1) {
-        if (checked == 1 && d < 0.02 * EIG_TOL) hint = steps > 1 ? steps - 1 : 1;
+        if (checked == 1 && d < 0.02 * SMALL_EIG_TOL) hint = steps > 1 ? steps - 1 : 1;
         else hint = steps;
     } else {                                       // uniform across the CTA (every warp solved the same matrix)
         if constexpr (NW > 1) __syncthreads();
@@ -415,7 +421,7 @@ __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_re
 }
 
 template <int P, int NW, bool RES>
-__global__ void __launch_bounds__(NW * 32, 16 / NW) nmfoa_small_kernel(const KArgs a) {
+__global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_small_kernel(const KArgs a) {
     extern __shared__ double smem[];
     using Cfg = SmallCfg<P>;
     constexpr int NT = NW * 32, CS = P + 2, TC = Cfg::TC;
