@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, "libdegnorm_b200.so")
 ABI_VERSION = 2
 DN_NCOUNTERS = 8
 DN_MAX_BINS = 64
-DN_MAX_SAMPLES = 128
+DN_MAX_SAMPLES = 256
 CNT_EXIT, CNT_N_HICOV, CNT_NMF_CALLS, CNT_SUM_COLS, CNT_EIG_STEPS, CNT_DROPS_LO, CNT_DROPS_HI, CNT_RESIDENT = range(8)
 EXIT_NAMES = {0: "none", 1: "few_hicov", 2: "empty_sample", 3: "median", 4: "no_selection", 5: "refined",
               6: "fallback_high", 7: "fallback", -1: "plan_error"}

@@ -263,7 +263,8 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
         return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
     a.pp = d.pp;
     a.ch = d.ch; a.ldm = d.ldm; a.ks = d.ks; a.g_in_smem = d.g_in_smem; a.ms_doubles = d.ms_doubles;
-    const long long g_d = (d.g_in_smem ? 2ll : 3ll) * d.pp * d.pp;
+    a.nsets = d.nsets; a.gacc_doubles = d.gacc_doubles;
+    const long long g_d = (d.g_in_smem ? 2ll : 3ll) * d.pp * d.pp + d.gacc_doubles;
     const long long cols_d = mode == MODE_INIT ? plan->ws_cols : (2ll * prm->p + 2) * plan->ws_cols;
     a.ws_stride = (g_d + cols_d + 31) / 32 * 32;
     return dn_launch_tiled(a, plan, st);
@@ -327,7 +328,6 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         return DN_OK;
     }
     const Derived d = derive(prm->p);
-    if (d.ntiles > d.nt) return fail(DN_ERR_UNSUPPORTED, "%sp = %lld needs more Gram tiles than threads", "", prm->p);
     plan->tile = d.tr;
     plan->threads = d.nt;
     plan->chunk_cols = d.ch;
@@ -355,7 +355,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
     if (ctas > n_work) ctas = n_work;
     if (ctas < 1) ctas = 1;
     plan->ctas = (int32_t)ctas;
-    const long long g_d = (d.g_in_smem ? 2ll : 3ll) * d.pp * d.pp;
+    const long long g_d = (d.g_in_smem ? 2ll : 3ll) * d.pp * d.pp + d.gacc_doubles;
     const long long cols_d = for_init ? plan->ws_cols : (2ll * prm->p + 2) * plan->ws_cols;
     const long long stride = (g_d + cols_d + 31) / 32 * 32;
     plan->ws_bytes = 256 + ctas * stride * 8;

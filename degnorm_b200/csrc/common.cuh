@@ -56,6 +56,8 @@ struct KArgs {
     const double *row_max;  // n x p row maxima of the raw coverage (from the init pass) or NULL
     double *row_max_out;    // init pass: where to write them (or NULL)
     int eig_hint;           // small path: adaptive blind power steps on/off
+    int nsets;              // tiled path: ceil(Gram tiles / threads); > 1 parks accumulators in global scratch
+    long long gacc_doubles; // tiled path: size of that scratch per CTA
 };
 
 namespace {

@@ -25,7 +25,7 @@ __host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, long long m
     return c;
 }
 
-struct Derived { int tr, nt, pp, ntiles, ch, ldm, ks, g_in_smem, ms_doubles; long long fixed_doubles; };
+struct Derived { int tr, nt, pp, ntiles, ch, ldm, ks, g_in_smem, ms_doubles, nsets; long long fixed_doubles, gacc_doubles; };
 
 inline int tile_for_p(int p) { return p <= 64 ? 4 : 8; }
 
@@ -42,6 +42,8 @@ inline Derived derive(int p) {
     if (ch > d.nt) ch = d.nt;
     d.ch = ch;
     d.ldm = ch + 1;
+    d.nsets = (d.ntiles + d.nt - 1) / d.nt;
+    d.gacc_doubles = d.nsets > 1 ? ((long long)d.ntiles * d.tr * d.tr + 31) / 32 * 32 : 0;
     int ks = d.nt / d.ntiles;
     const long long cap = (long long)d.pp * d.ldm / ((long long)d.ntiles * d.tr * d.tr);
     if (ks > cap) ks = (int)cap;

@@ -44,6 +44,7 @@ struct Gene {
     int eig_steps;
     int eig_fallbacks;
     double *B0;      // 2 * pp * pp doubles of global scratch for the small-gap eigen fallback
+    double *gacc;    // ntiles * TR * TR doubles of global scratch: Gram accumulators when tiles > threads
 };
 
 __device__ __forceinline__ int phys_col(const Gene &g, int vc) {
@@ -169,6 +170,49 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
             }
         }
         __syncthreads();
+        if (a.nsets > 1) {
+            // more Gram tiles than threads: every thread sweeps its tile of each set over the chunk, with the
+            // accumulators of all tiles parked in the CTA's global scratch between chunks
+            const int ntg_ = pp / TR;
+            const int ntl_ = ntg_ * (ntg_ + 1) / 2;
+            for (int set = 0; set < a.nsets; ++set) {
+                const int tile = set * NT + tid;
+                if (tile < ntl_) {
+                    int t = tile, si = 0;
+                    while (t >= ntg_ - si) { t -= ntg_ - si; ++si; }
+                    const int sj = si + t;
+                    double *ga = g.gacc + (long long)tile * (TR * TR);
+                    if (base == 0) {
+#pragma unroll
+                        for (int r = 0; r < TR; ++r)
+#pragma unroll
+                            for (int q = 0; q < TR; ++q) acc[r][q] = 0.0;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < TR; ++r)
+#pragma unroll
+                            for (int q = 0; q < TR; ++q) acc[r][q] = ga[r * TR + q];
+                    }
+                    const double *ma = g.ms + (si * TR) * ldm;
+                    const double *mb = g.ms + (sj * TR) * ldm;
+                    for (int cidx = 0; cidx < ncol; ++cidx) {
+                        double av[TR], bv[TR];
+#pragma unroll
+                        for (int r = 0; r < TR; ++r) av[r] = ma[r * ldm + cidx];
+#pragma unroll
+                        for (int r = 0; r < TR; ++r) bv[r] = mb[r * ldm + cidx];
+#pragma unroll
+                        for (int r = 0; r < TR; ++r)
+#pragma unroll
+                            for (int q = 0; q < TR; ++q) acc[r][q] = fma(av[r], bv[q], acc[r][q]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < TR; ++r)
+#pragma unroll
+                        for (int q = 0; q < TR; ++q) ga[r * TR + q] = acc[r][q];
+                }
+            }
+        } else
         // phase B: register-tiled SYRK out of the shared tile
         if (tile_ok) {
             const double *ma = g.ms + (ti * TR) * ldm;
@@ -190,7 +234,19 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
     // reduce the k-slices and mirror into the full square G (pp x pp)
     const int ntg = pp / TR;
     const int ntiles = ntg * (ntg + 1) / 2;
-    if (KS == 1) {
+    if (a.nsets > 1) {
+        __syncthreads();
+        for (int e = tid; e < ntiles * TR * TR; e += NT) {
+            const double sacc = g.gacc[e];
+            const int tile_e = e / (TR * TR), rq = e - tile_e * (TR * TR);
+            int t = tile_e, tii = 0;
+            while (t >= ntg - tii) { t -= ntg - tii; ++tii; }
+            const int tjj = tii + t;
+            const int i = tii * TR + rq / TR, j = tjj * TR + rq % TR;
+            g.G[(long long)i * pp + j] = sacc;
+            if (tii != tjj) g.G[(long long)j * pp + i] = sacc;
+        }
+    } else if (KS == 1) {
         if (tile_ok) {
 #pragma unroll
             for (int r = 0; r < TR; ++r)
@@ -379,6 +435,8 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
         g.G = slab + slab_o;
         slab_o += (long long)pp * pp;
     }
+    g.gacc = slab + slab_o;
+    if (a.nsets > 1) slab_o += a.gacc_doubles;
     g.eig_steps = 0;
     g.eig_fallbacks = 0;
 

@@ -175,7 +175,8 @@ class ShardEngine(object):
             prev = tier
         rest = np.flatnonzero(left)
         if len(rest):
-            self.buckets.append(self._bucket(rest, cand, -1))
+            # wholly streamed: a small shared-memory footprint lets several CTAs share an SM
+            self.buckets.append(self._bucket(rest, cand, 0))
 
     # ---------------------------------------------------------------------------------------------------------
     def _allreduce(self, t):

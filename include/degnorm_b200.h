@@ -30,7 +30,7 @@ extern "C" {
 
 #define DN_ABI_VERSION 2
 #define DN_MAX_BINS 64      /* baseline-selection bins held in the fused kernel (reference default: 20) */
-#define DN_MAX_SAMPLES 128  /* p supported by the fused kernels in this round */
+#define DN_MAX_SAMPLES 256  /* p supported by the fused kernels (one thread per sample in the n x p steps) */
 #define DN_NCOUNTERS 8      /* int32 counters per gene, see dn_counter */
 
 typedef enum dn_status {

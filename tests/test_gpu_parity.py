@@ -89,6 +89,8 @@ def _oracle(mats, reads, **kwargs):
     (17, 5, dict(degnorm_iter=1, nmf_iter=30)),
     (48, 4, dict(degnorm_iter=1, nmf_iter=25)),
     (70, 3, dict(degnorm_iter=1, nmf_iter=10)),
+    (130, 2, dict(degnorm_iter=1, nmf_iter=6)),
+    (200, 2, dict(degnorm_iter=1, nmf_iter=5)),       # more Gram tiles than threads (multi-set path)
 ])
 def test_against_oracle_across_sample_counts(p, n_genes, kwargs):
     from degnorm_b200.synth import synth_numpy

@@ -93,6 +93,9 @@ def test_plan_is_pure_host_arithmetic():
     bad = Params().to_c(1)
     assert lib.dn_make_plan(C.byref(bad), 128, 10, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
     assert b"2 samples" in lib.dn_last_error()
+    p200 = Params().to_c(200)
+    assert lib.dn_make_plan(C.byref(p200), 3000, 100, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert plan.tile == 8 and plan.resident_cols == 0 and plan.ws_bytes > 0
     big = Params().to_c(5000)
     assert lib.dn_make_plan(C.byref(big), 128, 10, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_UNSUPPORTED
 
