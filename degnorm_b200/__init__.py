@@ -3,3 +3,4 @@ __version__ = "0.1.0"
 
 from .nmf import GeneNMFOA          # noqa: F401
 from .engine import Params, ShardEngine, draw_offsets   # noqa: F401
+from .nmf_mpi import run_gene_nmfoa_mpi   # noqa: F401

@@ -1,0 +1,104 @@
+"""
+Multi-worker plumbing of the NMF-OA path: how genes are partitioned over workers (one process per GPU) and the one
+small exchange the algorithm needs -- the sum of 3p+1 per-sample doubles between outer iterations
+(reference: degnorm/nmf_mpi.py:603-629 gene scatter, :690-713 and :797-838 star gathers through rank 0, which
+this replaces by an all-reduce; every rank then derives the same scale factors redundantly).
+
+Communicator adapters give the engine one interface over
+  * an mpi4py-style communicator (what degnorm_mpi passes: `.rank`, `.size`, lowercase pickled send/recv/allreduce),
+  * a torch.distributed process group (NCCL on GPUs, gloo in CPU tests),
+  * no communicator at all (one worker).
+"""
+import numpy as np
+
+
+def partition_bounds(n_genes, size):
+    """Contiguous gene blocks per worker, exactly utils.split_into_chunks(all_genes, n=size) (utils.py:176-192,
+    used at nmf_mpi.py:605-606): chunk size ceil(n/size); trailing workers may get nothing."""
+    size = max(1, int(size))
+    cs = int(np.ceil(n_genes / float(size))) if n_genes else 0
+    out = []
+    for w in range(size):
+        lo = min(w * cs, n_genes)
+        out.append((lo, min(lo + cs, n_genes)))
+    return out
+
+
+class SoloComm(object):
+    rank, size = 0, 1
+
+    def allreduce_(self, t):
+        return t
+
+    def send_obj(self, obj, dest, tag=0):
+        raise RuntimeError("single worker")
+
+    def recv_obj(self, source, tag=0):
+        raise RuntimeError("single worker")
+
+    def barrier(self):
+        pass
+
+
+class MPIComm(object):
+    """mpi4py communicator (or anything with the same lowercase object API, e.g. a test double)."""
+
+    def __init__(self, comm):
+        self.comm = comm
+        self.rank = comm.rank if hasattr(comm, "rank") else comm.Get_rank()
+        self.size = comm.size if hasattr(comm, "size") else comm.Get_size()
+
+    def allreduce_(self, t):
+        # 3p+1 doubles: host round trip through the pickled allreduce (latency only)
+        if self.size > 1:
+            import torch
+            host = t.detach().cpu().numpy()
+            tot = self.comm.allreduce(host)          # default op: SUM
+            t.copy_(torch.from_numpy(np.asarray(tot, dtype=np.float64)))
+        return t
+
+    def send_obj(self, obj, dest, tag=0):
+        self.comm.send(obj, dest=dest, tag=tag)
+
+    def recv_obj(self, source, tag=0):
+        return self.comm.recv(source=source, tag=tag)
+
+    def barrier(self):
+        self.comm.Barrier()
+
+
+class TorchComm(object):
+    """torch.distributed process group; all_reduce runs on the tensor's device (NCCL) or through gloo."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+
+    def allreduce_(self, t):
+        if self.size > 1:
+            self.dist.all_reduce(t, group=self.group)
+        return t
+
+    def send_obj(self, obj, dest, tag=0):
+        self.dist.send_object_list([obj], dst=dest, group=self.group)
+
+    def recv_obj(self, source, tag=0):
+        box = [None]
+        self.dist.recv_object_list(box, src=source, group=self.group)
+        return box[0]
+
+    def barrier(self):
+        self.dist.barrier(group=self.group)
+
+
+def adapt(comm):
+    if comm is None:
+        return SoloComm()
+    if isinstance(comm, (SoloComm, MPIComm, TorchComm)):
+        return comm
+    if hasattr(comm, "send") and hasattr(comm, "recv"):
+        return MPIComm(comm)
+    return TorchComm(comm)

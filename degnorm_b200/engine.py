@@ -72,11 +72,13 @@ class _Bucket(object):
 class ShardEngine(object):
     """One GPU's shard.  load() takes device tensors; run() leaves device tensors in self.out."""
 
-    def __init__(self, prm, p, device, group=None, force_streamed=False, small_tiers=None, use_row_max=True):
+    def __init__(self, prm, p, device, group=None, force_streamed=False, small_tiers=None, use_row_max=True,
+                 allreduce=None):
         self.prm = prm
         self.p = int(p)
         self.device = torch.device(device)
         self.group = group
+        self.allreduce = allreduce       # callable(tensor) summing in place over the workers (distributed.py)
         self.force_streamed = force_streamed
         self.small_tiers = small_tiers
         self.serial_buckets = False
@@ -103,7 +105,7 @@ class ShardEngine(object):
         if self.n and int(self.lengths.max()) >= 2 ** 31 - 1:
             raise ValueError("gene longer than 2^31-2 positions")
         self.off_dev = torch.from_numpy(self.offsets_np).to(self.device)
-        self.reads = reads.contiguous()
+        self.reads = reads.contiguous() if self.n > 0 else torch.zeros((1, self.p), dtype=torch.float64, device=self.device)
         self._plan()
 
     def _make_plan(self, max_cols, n_work, want_resident, for_init=False, warps=0):
@@ -180,7 +182,9 @@ class ShardEngine(object):
 
     # ---------------------------------------------------------------------------------------------------------
     def _allreduce(self, t):
-        if self.group is not None:
+        if self.allreduce is not None:
+            self.allreduce(t)
+        elif self.group is not None:
             torch.distributed.all_reduce(t, group=self.group)
 
     def run(self, ds_offsets=None, want_estimates=True):
