@@ -172,6 +172,14 @@ class Clocks(threading.Thread):
 # ------------------------------------------------------------------------------------------------ main
 def main():
     args = parse()
+    # libraries (NCCL's version banner) write to fd 1: park the real stdout and hand fd 1 to stderr until the JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
     from degnorm_b200.synth import CONFIGS, config_lengths
     cfg = dict(CONFIGS[args.config])
     cfg["name"] = args.config
@@ -200,10 +208,10 @@ def main():
             vals.append(cb["value"])
         v = float(np.mean(vals))
         cb["value"] = v
-        print(json.dumps(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+        emit(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                               ms_per_step=1000.0 * n_sample / v, higher_is_better=True, scaling="weak", vs_baseline=None,
                               dtype="f64", data="synthetic", config=config, impl="reference", cpu_baseline=cb,
-                              e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+                              e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0))
         return
 
     import torch
@@ -342,11 +350,11 @@ def main():
         cb = None
         if not args.no_cpu:
             cb = run_cpu_baseline(cfg, kw, args.cpu_genes or 2 * cores, cores)
-        print(json.dumps(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        emit(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                               ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                               dtype="f64", data="synthetic", config=config, e2e=e2e, gpu_launches=launches,
                               roofline=roofline, cpu_baseline=cb, clocks=clock_summary,
-                              algorithmic_bytes_per_step=total_bytes, algorithmic_parts=parts)))
+                              algorithmic_bytes_per_step=total_bytes, algorithmic_parts=parts))
     if world > 1:
         dist.destroy_process_group()
 

@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdegnorm_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 DN_NCOUNTERS = 8
 DN_MAX_BINS = 64
 DN_MAX_SAMPLES = 256
@@ -25,7 +25,8 @@ class DnParams(C.Structure):
 
 class DnPlan(C.Structure):
     _fields_ = [("tile", C.c_int32), ("threads", C.c_int32), ("ctas", C.c_int32), ("resident_cols", C.c_int32),
-                ("chunk_cols", C.c_int32), ("smem_bytes", C.c_int32), ("ws_cols", C.c_int64), ("ws_bytes", C.c_int64)]
+                ("chunk_cols", C.c_int32), ("smem_bytes", C.c_int32), ("cluster", C.c_int32), ("reserved", C.c_int32),
+                ("ws_cols", C.c_int64), ("ws_bytes", C.c_int64)]
 
 
 class DegnormCudaError(RuntimeError):
@@ -40,7 +41,7 @@ _SIGS = {
     "dn_last_error": (C.c_char_p, []),
     "dn_device_info": (C.c_int, [C.POINTER(C.c_int32)] * 3),
     "dn_make_plan": (C.c_int, [C.POINTER(DnParams), C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                               C.c_int32, C.POINTER(DnPlan)]),
+                               C.c_int32, C.c_int32, C.POINTER(DnPlan)]),
     "dn_init_ratio_svd": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P, _P,
                                     C.c_int64, _P]),
     "dn_baseline_selection": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P,

@@ -291,12 +291,34 @@ int dn_device_info(int32_t *sm_count, int32_t *max_smem_optin, int32_t *cc) {
 }
 
 int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t want_resident, int32_t for_init,
-                 int32_t warps, int32_t sm_count, int32_t max_smem_optin, dn_plan *plan) {
+                 int32_t warps, int32_t cluster, int32_t sm_count, int32_t max_smem_optin, dn_plan *plan) {
     int rc = check_params(prm);
     if (rc) return rc;
     if (!plan || max_cols < 1 || sm_count < 1 || max_smem_optin < 16 * 1024) return fail(DN_ERR_INVALID, "bad planning argument%s");
     memset(plan, 0, sizeof(*plan));
+    plan->cluster = 1;
     const int P = for_init ? 0 : small_P(prm->p);
+    if (P > 0 && cluster > 1) {
+        // ---- small-p path, one thread-block cluster per gene: every CTA holds ceil(max_cols / cluster) columns
+        if (cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) return fail(DN_ERR_INVALID, "cluster must be 2, 4, 8 or 16%s");
+        const long long per_col = 8ll * (2 * small_cs(P) + 2);
+        long long share = (max_cols + cluster - 1) / cluster;
+        share = (share + 7) / 8 * 8;
+        const long long fixed_b = small_carve(P, SMALL_CLU_WARPS, 0, true).total * 8;
+        const bool res = want_resident != 0 && fixed_b + share * per_col <= max_smem_optin;
+        plan->tile = 0;
+        plan->threads = SMALL_CLU_WARPS * 32;
+        plan->cluster = cluster;
+        plan->resident_cols = res ? (int32_t)share : 0;
+        plan->smem_bytes = (int32_t)(small_carve(P, SMALL_CLU_WARPS, res ? (int)share : 0, true).total * 8);
+        plan->ws_cols = res ? 0 : share;
+        long long clusters = sm_count / cluster;                     // one CTA per SM (256 threads, up to 216 registers)
+        if (clusters > n_work) clusters = n_work;
+        if (clusters < 1) clusters = 1;
+        plan->ctas = (int32_t)(clusters * cluster);
+        plan->ws_bytes = 256 + (long long)plan->ctas * small_slab_doubles(P, plan->ws_cols) * 8;
+        return DN_OK;
+    }
     if (P > 0) {
         // ---- small-p path: a bucket is either wholly shared-memory resident or wholly streamed
         const long long per_col = 8ll * (2 * small_cs(P) + 2);

@@ -62,12 +62,14 @@ __host__ __device__ inline int small_P(int p) { return p <= 4 ? 4 : (p <= 8 ? 8 
 __host__ __device__ inline int small_cs(int P) { return P + 2; }
 constexpr int SMALL_GPART = 96;       // doubles per warp of partial Gram / reduction scratch
 constexpr int SMALL_MAX_WARPS = 16;
+constexpr int SMALL_CLMAX = 16;       // largest thread-block cluster per gene (non-portable size)
+constexpr int SMALL_CLU_WARPS = 8;    // warps per CTA of the cluster kernels
 
 struct SmallCarve {
-    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, X, M, resb, tb, total;   // offsets in doubles
+    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, lw, xbuf, X, M, resb, tb, total;   // offsets in doubles
 };
 
-__host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_cols) {
+__host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_cols, bool clu = false) {
     SmallCarve c;
     long long o = 0;
     c.small = o; o += (long long)N_SMALL * P;
@@ -79,6 +81,8 @@ __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_co
     c.vx = o;    o += (long long)nw * 2 * P;
     c.gpart = o; o += (long long)(nw > 1 ? 2 : 1) * nw * SMALL_GPART;   // two alternating partial-sum buffers
     c.tab = o;   o += 32;                       // 16 tiles x 4 ints
+    c.lw = o;    o += DN_MAX_BINS / 2;          // per-bin local widths (ints)
+    c.xbuf = o;  o += clu ? 2ll * SMALL_CLMAX * SMALL_GPART : 0;   // cluster exchange slots
     const long long cs = small_cs(P);
     c.X = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
     c.M = o;     o += resident_cols > 0 ? cs * resident_cols : 0;

@@ -19,10 +19,19 @@
 //   * dropping a bin physically rotates its columns to the end of the buffer, so the current matrix is always the
 //     contiguous range [0, n_cur): no per-column index mapping in the inner loop.
 //
+//   * long genes (CLU = true): a thread-block CLUSTER owns the gene.  Each CTA keeps a contiguous slice of the
+//     kept columns in its own shared memory (or slab) and runs phases A/B on it; the only cross-CTA traffic in
+//     the inner iteration is the 96-double partial Gram, written straight into every peer's shared memory
+//     (DSMEM) and followed by ONE cluster barrier; every CTA then sums the slots in rank order and solves
+//     redundantly, so all CTAs take bit-identical decisions.  Row sums, residual bin sums and column counts
+//     use the same all-to-all exchange.
+//
 // No tensor cores: fp64 FMA pipe only.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "launch.h"
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -50,6 +59,10 @@ struct SGene {
     int n0, n_cur, cs, nb0, nalive;
     int eig_steps, eig_fallbacks, gpar;
     double *B0;
+    // cluster state (CLU kernels; a lone CTA is rank 0 of 1): n0 / n_cur are this CTA's columns, n0g / n_curg the gene's
+    double *xbuf;       // exchange slots: 2 alternating sets of SMALL_CLMAX x SMALL_GPART doubles (peers write here)
+    int *lw;            // this CTA's width of every original bin
+    int crank, csize, xpar, n0g, n_curg, goff;
     int tpack;      // this lane's Gram tile: r0 | offA << 4 | offB << 8 | u0 << 12 | u1 << 16 | u2 << 20; -1: none
 };
 
@@ -88,6 +101,34 @@ __device__ __forceinline__ double dot_v(const double (&v)[P], const double (&m)[
     return t0 + t1;
 }
 
+// All-to-all sum over the cluster of n <= SMALL_GPART doubles (`vals`: local shared memory, already published
+// to the CTA): every CTA writes its values into its slot in every peer (DSMEM), one cluster barrier, every CTA adds
+// the slots in rank order -> bit-identical `out` everywhere.  Slot sets alternate, so one barrier per call is enough.
+template <int NT>
+__device__ __forceinline__ void clu_allsum(SGene &g, const double *vals, int n, double *out) {
+    cg::cluster_group cl = cg::this_cluster();
+    double *buf = g.xbuf + g.xpar * (SMALL_CLMAX * SMALL_GPART);
+    g.xpar ^= 1;
+    for (int e = threadIdx.x; e < n * g.csize; e += NT) {
+        const int r = e / n, k = e - r * n;
+        *cl.map_shared_rank(buf + g.crank * SMALL_GPART + k, r) = vals[k];
+    }
+    cl.sync();
+    for (int k = threadIdx.x; k < n; k += NT) {
+        double s = 0.0;
+        for (int r = 0; r < g.csize; ++r) s += buf[r * SMALL_GPART + k];
+        out[k] = s;
+    }
+    __syncthreads();
+}
+
+// local start of alive bin k in this CTA's current columns
+__device__ __forceinline__ int lstart(const SGene &g, int k) {
+    int s = 0;
+    for (int q = 0; q < k; ++q) s += g.lw[g.alive[q]];
+    return s;
+}
+
 // sums NV per-thread values over the CTA (fixed tree: warp shuffles, then warps in order) into out[0..NV)
 template <int NV, int NW>
 __device__ __forceinline__ void block_sum_vec(double (&x)[NV], double *part, double *out) {
@@ -120,7 +161,7 @@ __device__ __forceinline__ void block_sum_vec(double (&x)[NV], double *part, dou
 // ---- one pass: (optional multiplier update of this warp's columns) + Gram of M -----------------------------------
 // UPDATE=false: G = M M^T with M = x (first rank-one fit, nmf.py:88).
 // UPDATE=true : lambda <- max(0, lambda - c (K E - x)), M = x + lambda, G = M M^T (nmf.py:93-98); K E = v (v.M_old).
-template <int P, int NW, bool UPDATE>
+template <int P, int NW, bool UPDATE, bool CLU>
 __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const double (&v)[P]) {
     using Cfg = SmallCfg<P>;
     constexpr int TC = Cfg::TC, KS = Cfg::KS, NTP = Cfg::NTP, NTILE = Cfg::NTILE, CS = P + 2, NT = NW * 32;
@@ -212,11 +253,32 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
                 for (int q = 0; q < TC; ++q) gp[warp * SMALL_GPART + lane * (2 * TC) + r * TC + q] = acc[r][q];
         }
         __syncthreads();
+        const double *src = gp;
+        int nsrc = NW;
+        if constexpr (CLU) {
+            // CTA sum of the warp partials, written straight into this CTA's slot in every peer; one cluster barrier
+            cg::cluster_group cl = cg::this_cluster();
+            double *buf = g.xbuf + g.xpar * (SMALL_CLMAX * SMALL_GPART);
+            g.xpar ^= 1;
+            for (int e = tid; e < NTILE * 2 * TC; e += NT) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += gp[w * SMALL_GPART + e];
+                for (int r = 0; r < g.csize; ++r) *cl.map_shared_rank(buf + g.crank * SMALL_GPART + e, r) = s;
+            }
+            cl.sync();
+            src = buf;
+            nsrc = g.csize;
+        }
         double *Gw = g.G + warp * (P * P);
         for (int e = lane; e < NTILE * 2 * TC; e += 32) {
             double s = 0.0;
+            if constexpr (CLU) {
+                for (int w = 0; w < nsrc; ++w) s += src[w * SMALL_GPART + e];
+            } else {
 #pragma unroll
-            for (int w = 0; w < NW; ++w) s += gp[w * SMALL_GPART + e];
+                for (int w = 0; w < NW; ++w) s += gp[w * SMALL_GPART + e];
+            }
             const int t = e / (2 * TC), rq = e - t * (2 * TC);
             const int r = rq / TC, q = rq - r * TC;
             const int i = g.tab[t * 4] + r, j = g.tab[t * 4 + 1 + q];
@@ -340,7 +402,7 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
 }
 
 // ---- final pass of an nmf() call (see final_pass in nmfoa_tiled.cu for what each sum is) ----------------------
-template <int P, int NW>
+template <int P, int NW, bool CLU>
 __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P], bool first, bool want_res,
                                  double *e_first_g) {
     constexpr int NT = NW * 32, CS = P + 2, NV = 2 + 2 * P;
@@ -377,11 +439,12 @@ __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P],
             if (lane == k) g.v[k] = v[k];
     }
     block_sum_vec<NV, NW>(acc, g.gpart, g.red);       // (its barriers also publish tb / resb / v)
+    if constexpr (CLU) clu_allsum<NT>(g, g.red, NV, g.red);
     const double sum_t = g.red[0], sum_t2 = g.red[1];
     const double sigma = sqrt(sum_t2);
     if (e_first_g != nullptr) {                          // E of the first fit (only when no column was filtered)
         const double inv = sigma > 0.0 ? 1.0 / sigma : 0.0;
-        for (int col = tid; col < n; col += NT) e_first_g[col] = g.tb[col] * inv;
+        for (int col = tid; col < n; col += NT) e_first_g[g.goff + col] = g.tb[col] * inv;
     }
     if (tid < P) {
         const double vi = g.v[tid];
@@ -394,7 +457,7 @@ __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P],
 }
 
 // nmf() on the current columns [0, n_cur) (nmf.py:78-107).  Leaves v, K, tmp = rs(KE), rsF, rsC, resb, tb.
-template <int P, int NW>
+template <int P, int NW, bool CLU>
 __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_res, double *e_first_g) {
     constexpr int NT = NW * 32, CS = P + 2;
     const int tid = threadIdx.x;
@@ -410,24 +473,24 @@ __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_re
     for (int k = 0; k < P; ++k) v[k] = 0.0;
     double inv_lam = 1.0;
     int hint = 0;
-    gram_small<P, NW, false>(a, g, v);
+    gram_small<P, NW, false, CLU>(a, g, v);
     eig_small<P, NW>(a, g, v, true, inv_lam, hint);
     const int T = a.nmf_iter;
     for (int it = 0; it < T; ++it) {
-        gram_small<P, NW, true>(a, g, v);
+        gram_small<P, NW, true, CLU>(a, g, v);
         eig_small<P, NW>(a, g, v, false, inv_lam, hint);
     }
-    final_pass_small<P, NW>(a, g, v, first, want_res, e_first_g);
+    final_pass_small<P, NW, CLU>(a, g, v, first, want_res, e_first_g);
 }
 
-template <int P, int NW, bool RES>
+template <int P, int NW, bool RES, bool CLU>
 __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_small_kernel(const KArgs a) {
     extern __shared__ double smem[];
     using Cfg = SmallCfg<P>;
     constexpr int NT = NW * 32, CS = P + 2, TC = Cfg::TC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p;
-    const SmallCarve cv = small_carve(P, NW, RES ? a.resident_cols : 0);
+    const SmallCarve cv = small_carve(P, NW, RES ? a.resident_cols : 0, CLU);
 
     SGene g;
     double *sm = smem + cv.small;
@@ -441,9 +504,17 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
     g.vx = smem + cv.vx;
     g.gpart = smem + cv.gpart;
     g.tab = reinterpret_cast<int *>(smem + cv.tab);
+    g.lw = reinterpret_cast<int *>(smem + cv.lw);
+    g.xbuf = smem + cv.xbuf;
+    g.crank = 0; g.csize = 1; g.xpar = 0;
+    if constexpr (CLU) {
+        cg::cluster_group cl = cg::this_cluster();
+        g.crank = (int)cl.block_rank();
+        g.csize = (int)cl.num_blocks();
+    }
     double *slab = a.ws + (long long)blockIdx.x * a.ws_stride;
     g.B0 = slab;
-    const int cap = RES ? a.resident_cols : (int)a.ws_ld;
+    const int cap = RES ? a.resident_cols : (int)a.ws_ld;          // columns one CTA can hold
     if constexpr (RES) {
         g.X = smem + cv.X; g.M = smem + cv.M; g.resb = smem + cv.resb; g.tb = smem + cv.tb;
     } else {
@@ -470,10 +541,21 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
     g.eig_fallbacks = 0;
     g.gpar = 0;
     __syncthreads();
+    if constexpr (CLU) cg::this_cluster().sync();        // peers' shared memory is live before anyone writes to it
 
     for (;;) {
-        if (tid == 0) g.ibuf[0] = atomicAdd(a.queue, 1);
-        __syncthreads();
+        // one queue ticket per gene: a lone CTA takes it itself, a cluster's rank 0 hands it to every peer
+        if constexpr (CLU) {
+            cg::cluster_group cl = cg::this_cluster();
+            if (g.crank == 0 && tid == 0) {
+                const int t = atomicAdd(a.queue, 1);
+                for (int r = 0; r < g.csize; ++r) *cl.map_shared_rank(g.ibuf, r) = t;
+            }
+            cl.sync();
+        } else {
+            if (tid == 0) g.ibuf[0] = atomicAdd(a.queue, 1);
+            __syncthreads();
+        }
         const int w = g.ibuf[0];
         __syncthreads();
         if (w >= a.n_work) break;
@@ -503,27 +585,31 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
         const double gmax = block_max<NT>(tmax, g.red);
         const double thr = 0.1 * gmax;                                   // nmf.py:76
         // (2) keep the columns that are high coverage (strict >) and on the systematic sample (nmf.py:220-229),
-        //     scaled, compacted in order into the working buffer
+        //     scaled, compacted in order into the working buffer.  In a cluster every CTA takes a contiguous
+        //     share of the candidates.
         const int rate = a.rate;
         const int start = (rate > 1 && a.ds_start) ? a.ds_start[gid] : 0;
         const int ncand = start < L ? (L - start + rate - 1) / rate : 0;
+        const int share = (ncand + g.csize - 1) / g.csize;
+        const int k_lo = min(g.crank * share, ncand), k_hi = min(k_lo + share, ncand);
         int exit_code = DN_EXIT_NONE;
         int ran = 0, nmf_calls = 0, sum_cols = 0;
         unsigned long long drops = 0ull;
         bool k_is_refined = false;
-        int n0 = 0;
-        if (ncand > cap) {
+        int n0 = 0;              // kept columns of the whole gene
+        g.goff = 0;
+        if (share > cap) {
             exit_code = -1;                    // planner error: the bucket's tier is too small for this gene
         } else {
             int running = 0;
             int *wcount = g.ibuf + 1;        // NW ints
-            for (int kb = 0; kb < ncand; kb += NT) {
+            for (int kb = k_lo; kb < k_hi; kb += NT) {
                 const int k = kb + tid;
                 bool keep = false;
                 double xv[P];
 #pragma unroll
                 for (int i = 0; i < P; ++i) xv[i] = 0.0;
-                if (k < ncand) {
+                if (k < k_hi) {
                     const long long col = start + (long long)k * rate;
                     double cm = -1.0e300;
 #pragma unroll
@@ -559,26 +645,41 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 if constexpr (NW > 1) __syncthreads();
             }
             bsync<NW>();
+            g.n0 = g.n_cur = running;
             n0 = running;
+            if constexpr (CLU) {
+                // column counts of every CTA -> gene total and this CTA's global offset
+                if (tid < g.csize) g.binm[tid] = tid == g.crank ? (double)running : 0.0;
+                __syncthreads();
+                clu_allsum<NT>(g, g.binm, g.csize, g.binm);
+                n0 = 0;
+                for (int r = 0; r < g.csize; ++r) {
+                    if (r == g.crank) g.goff = n0;
+                    n0 += (int)g.binm[r];
+                }
+                __syncthreads();
+            }
         }
+        g.n0g = g.n_curg = n0;
         if (exit_code == -1) {
             // nothing: reported through the counters
         } else if (n0 < a.min_hi) {
             exit_code = DN_EXIT_FEW_HICOV;                               // nmf.py:232-233
         } else {
-            g.n0 = g.n_cur = n0;
             g.cs = n0; g.nb0 = 1; g.nalive = 1;
+            if (tid == 0) { g.alive[0] = 0; g.lw[0] = g.n0; }
             {   // rs(F_start)
                 double rs[P];
 #pragma unroll
                 for (int i = 0; i < P; ++i) rs[i] = 0.0;
-                for (int col = tid; col < n0; col += NT) {
+                for (int col = tid; col < g.n0; col += NT) {
                     double x[P];
                     load_col<P>(g.X + col * CS, x);
 #pragma unroll
                     for (int i = 0; i < P; ++i) rs[i] += x[i];
                 }
                 block_sum_vec<P, NW>(rs, g.gpart, g.rs0);
+                if constexpr (CLU) clu_allsum<NT>(g, g.rs0, P, g.rs0);
             }
             bool any_empty = false;
             for (int i = 0; i < p; ++i) any_empty |= !(g.rs0[i] > 0.0);
@@ -590,8 +691,8 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 bool first = true, in_loop = false;
                 double rmax = 0.0;
                 for (;;) {
-                    run_nmf_small<P, NW>(a, g, first, true, (first && store_e) ? a.e_first + o0 : nullptr);
-                    nmf_calls += 1; sum_cols += g.n_cur;
+                    run_nmf_small<P, NW, CLU>(a, g, first, true, (first && store_e) ? a.e_first + o0 : nullptr);
+                    nmf_calls += 1; sum_cols += g.n_curg;
                     if (first) {
                         if (tid < P) {
                             g.rho[tid] = 1.0 - g.rs0[tid] / (g.tmp[tid] + 1.0);
@@ -613,8 +714,12 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                         g.cs = (n0 + a.bins - 1) / a.bins;               // utils.py:176-192
                         g.nb0 = (n0 + g.cs - 1) / g.cs;
                         g.nalive = g.nb0;
-                        if (tid < g.nb0) g.alive[tid] = tid;
-                        if (NT < DN_MAX_BINS && tid + NT < g.nb0) g.alive[tid + NT] = tid + NT;
+                        for (int b = tid; b < g.nb0; b += NT) {
+                            g.alive[b] = b;
+                            // this CTA's share of bin b: [b cs, (b+1) cs) cut to its global column range
+                            const int lo = max(b * g.cs, g.goff), hi = min(min((b + 1) * g.cs, n0), g.goff + g.n0);
+                            g.lw[b] = max(0, hi - lo);
+                        }
                         bsync<NW>();
                         in_loop = true;
                         first = false;
@@ -627,49 +732,54 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                         bsync<NW>();
                         rmax = g.rho[0];
                         for (int i = 1; i < p; ++i) rmax = fmax(rmax, g.rho[i]);
-                        if (g.nalive <= a.min_bins || g.n_cur < a.min_len) break;        // nmf.py:323
+                        if (g.nalive <= a.min_bins || g.n_curg < a.min_len) break;       // nmf.py:323
                     }
                     if (!(rmax > 0.1)) break;                            // nmf.py:273
                     ran = 1;
-                    // mean squared-relative-residual per alive bin (nmf.py:280-283); one warp per bin.
-                    // Alive bins are contiguous: bin k of the current matrix starts at column k * cs.
+                    // sum of the squared relative residuals per alive bin (nmf.py:280-283); one warp per bin.
+                    // Alive bins are contiguous in every CTA: bin k starts at lstart(k) and is lw[alive[k]] wide here.
                     for (int k = warp; k < g.nalive; k += NW) {
-                        const int b = g.alive[k];
-                        const int wdt = min(g.cs, g.n0 - b * g.cs);
-                        const double *rr = g.resb + k * g.cs;
+                        const int wl = g.lw[g.alive[k]];
+                        const double *rr = g.resb + lstart(g, k);
                         double s = 0.0;
-                        for (int j = lane; j < wdt; j += 32) s += rr[j];
+                        for (int j = lane; j < wl; j += 32) s += rr[j];
                         s = warp_sum(s);
-                        if (lane == 0) g.binm[k] = s / (double)wdt;
+                        if (lane == 0) g.binm[k] = s;
                     }
                     bsync<NW>();
+                    if constexpr (CLU) clu_allsum<NT>(g, g.binm, g.nalive, g.binm);
                     int kd = 0;
-                    double best = g.binm[0];
-                    for (int k = 1; k < g.nalive; ++k)
-                        if (g.binm[k] > best) { best = g.binm[k]; kd = k; }
+                    double best = -1.0;
+                    for (int k = 0; k < g.nalive; ++k) {
+                        const int b = g.alive[k];
+                        const double mean = g.binm[k] / (double)min(g.cs, n0 - b * g.cs);
+                        if (mean > best) { best = mean; kd = k; }
+                    }
                     if (best == 0.0) break;                              // nmf.py:286-287
                     const int bd = g.alive[kd];
-                    const int wd = min(g.cs, g.n0 - bd * g.cs);
-                    bsync<NW>();
-                    if (tid == 0)
-                        for (int k = kd; k < g.nalive - 1; ++k) g.alive[k] = g.alive[k + 1];
-                    {   // rotate the dropped bin's columns to the end of the current matrix (M is scratch)
-                        const int a0 = kd * g.cs;
-                        const int tail = g.n_cur - a0 - wd;
+                    const int wd = min(g.cs, n0 - bd * g.cs);
+                    {   // rotate this CTA's part of the dropped bin to the end of its current columns (M is scratch)
+                        const int a0 = lstart(g, kd);
+                        const int wl = g.lw[bd];
+                        const int tail = g.n_cur - a0 - wl;
                         const double2 *xs = reinterpret_cast<const double2 *>(g.X + (long long)a0 * CS);
                         double2 *ms = reinterpret_cast<double2 *>(g.M + (long long)a0 * CS);
                         const int h = CS / 2;
-                        for (int e = tid; e < (tail + wd) * h; e += NT) ms[e] = xs[e];
+                        bsync<NW>();
+                        for (int e = tid; e < (tail + wl) * h; e += NT) ms[e] = xs[e];
                         bsync<NW>();
                         double2 *xd = reinterpret_cast<double2 *>(g.X + (long long)a0 * CS);
-                        for (int e = tid; e < tail * h; e += NT) xd[e] = ms[wd * h + e];
-                        for (int e = tid; e < wd * h; e += NT) xd[tail * h + e] = ms[e];
+                        for (int e = tid; e < tail * h; e += NT) xd[e] = ms[wl * h + e];
+                        for (int e = tid; e < wl * h; e += NT) xd[tail * h + e] = ms[e];
+                        if (tid == 0)
+                            for (int k = kd; k < g.nalive - 1; ++k) g.alive[k] = g.alive[k + 1];
+                        g.n_cur -= wl;
                     }
                     bsync<NW>();
                     g.nalive -= 1;
-                    g.n_cur -= wd;
+                    g.n_curg -= wd;
                     drops |= 1ull << bd;
-                    if (g.n_cur < 2) break;                              // svds ValueError swallowed, nmf.py:306-310
+                    if (g.n_curg < 2) break;                             // svds ValueError swallowed, nmf.py:306-310
                 }
                 if (in_loop) {
                     bsync<NW>();
@@ -678,7 +788,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                     if (rmax < 0.2) {                                    // nmf.py:327-346
                         floor_abs(g.K, g.K, p);
                         double s = 0.0;
-                        for (int j = tid; j < n0; j += NT) {
+                        for (int j = tid; j < g.n0; j += NT) {
                             double x[P];
                             load_col<P>(g.X + j * CS, x);
                             double e = -1.0e300;
@@ -687,7 +797,14 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                                 if (i < p) e = fmax(e, x[i] / g.K[i]);
                             s += e;
                         }
-                        const double S = block_sum<NT>(s, g.red);
+                        double S = block_sum<NT>(s, g.red);
+                        if constexpr (CLU) {
+                            if (tid == 0) g.binm[0] = S;
+                            __syncthreads();
+                            clu_allsum<NT>(g, g.binm, 1, g.binm);
+                            S = g.binm[0];
+                            __syncthreads();
+                        }
                         if (tid < P) g.rho[tid] = 1.0 - g.rs0[tid] / (g.K[tid] * S + 1.0);
                         __syncthreads();
                         rmax = g.rho[0];
@@ -708,7 +825,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 }
             }
         }
-        // (5) outputs
+        // (5) outputs (rank 0 of a cluster; every CTA holds the same values)
         __syncthreads();
         const bool is_default = exit_code == DN_EXIT_FEW_HICOV || exit_code == DN_EXIT_EMPTY_SAMPLE ||
                                 exit_code == DN_EXIT_MEDIAN || exit_code == -1;
@@ -721,37 +838,68 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 floor_abs(g.K0, g.K, p);
             }
         }
-        if (tid < p) {
-            double r = is_default ? 0.0 : g.rho[tid];
-            r = r > 0.9 ? 0.9 : r;                                       // nmf.py:398-399
-            r = r < 0.0 ? 0.0 : r;
-            a.rho[(long long)gid * p + tid] = r;
-            if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
-        }
-        if (tid == 0) {
-            a.ran[gid] = (unsigned char)(is_default ? 0 : ran);
-            if (cnt) {
-                cnt[DN_CNT_EXIT] = exit_code; cnt[DN_CNT_N_HICOV] = n0; cnt[DN_CNT_NMF_CALLS] = nmf_calls;
-                cnt[DN_CNT_SUM_COLS] = sum_cols; cnt[DN_CNT_EIG_STEPS] = g.eig_steps;
-                cnt[DN_CNT_DROPS_LO] = (int)(drops & 0xffffffffull); cnt[DN_CNT_DROPS_HI] = (int)(drops >> 32);
-                cnt[DN_CNT_RESIDENT] = (int)RES | (g.eig_fallbacks << 1);
+        if (g.crank == 0) {
+            if (tid < p) {
+                double r = is_default ? 0.0 : g.rho[tid];
+                r = r > 0.9 ? 0.9 : r;                                   // nmf.py:398-399
+                r = r < 0.0 ? 0.0 : r;
+                a.rho[(long long)gid * p + tid] = r;
+                if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
+            }
+            if (tid == 0) {
+                a.ran[gid] = (unsigned char)(is_default ? 0 : ran);
+                if (cnt) {
+                    cnt[DN_CNT_EXIT] = exit_code; cnt[DN_CNT_N_HICOV] = n0; cnt[DN_CNT_NMF_CALLS] = nmf_calls;
+                    cnt[DN_CNT_SUM_COLS] = sum_cols; cnt[DN_CNT_EIG_STEPS] = g.eig_steps;
+                    cnt[DN_CNT_DROPS_LO] = (int)(drops & 0xffffffffull); cnt[DN_CNT_DROPS_HI] = (int)(drops >> 32);
+                    cnt[DN_CNT_RESIDENT] = (int)RES | (g.eig_fallbacks << 1);
+                }
             }
         }
         __syncthreads();
+        if constexpr (CLU) cg::this_cluster().sync();    // nobody re-uses a peer's ticket slot before it was read
     }
 }
 
 template <int P, int NW, bool RES>
 int launch_small_one(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
-    auto kern = nmfoa_small_kernel<P, NW, RES>;
+    auto kern = nmfoa_small_kernel<P, NW, RES, false>;
     DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
     kern<<<plan->ctas, NW * 32, plan->smem_bytes, st>>>(a);
     DN_CUDA(cudaGetLastError());
     return DN_OK;
 }
 
+// cluster launch: plan->cluster CTAs per gene, grid = whole clusters
+template <int P, bool RES>
+int launch_small_cluster(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+    auto kern = nmfoa_small_kernel<P, SMALL_CLU_WARPS, RES, true>;
+    DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+    if (plan->cluster > 8) DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(plan->ctas / plan->cluster * plan->cluster, 1, 1);
+    cfg.blockDim = dim3(SMALL_CLU_WARPS * 32, 1, 1);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = plan->cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DN_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    return DN_OK;
+}
+
 template <int P>
 int launch_small(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+    if (plan->cluster > 1) {
+        if (plan->threads != SMALL_CLU_WARPS * 32) return dn_fail(DN_ERR_INVALID, "cluster plans use 256 threads%s");
+        return plan->resident_cols > 0 ? launch_small_cluster<P, true>(a, plan, st)
+                                       : launch_small_cluster<P, false>(a, plan, st);
+    }
     if (plan->resident_cols > 0) {
         switch (plan->threads) {
             case 32: return launch_small_one<P, 1, true>(a, plan, st);

@@ -83,6 +83,9 @@ class ShardEngine(object):
         self.small_tiers = small_tiers
         self.serial_buckets = False
         self.prioritise = True
+        self.use_clusters = True
+        self.force_cluster = 0
+        self.clusters = (2, 4, 8, 16)
         self.bucket_starts = {}
         self.use_row_max = use_row_max
         self.cprm = prm.to_c(p)
@@ -108,18 +111,19 @@ class ShardEngine(object):
         self.reads = reads.contiguous() if self.n > 0 else torch.zeros((1, self.p), dtype=torch.float64, device=self.device)
         self._plan()
 
-    def _make_plan(self, max_cols, n_work, want_resident, for_init=False, warps=0):
+    def _make_plan(self, max_cols, n_work, want_resident, for_init=False, warps=0, cluster=0):
         plan = DnPlan()
         check(self.lib.dn_make_plan(C.byref(self.cprm), int(max_cols), int(n_work), int(want_resident),
-                                    int(for_init), int(warps), self.sm_count, self.max_smem, C.byref(plan)))
+                                    int(for_init), int(warps), int(cluster), self.sm_count, self.max_smem,
+                                    C.byref(plan)))
         return plan
 
-    def _bucket(self, ids, cand, want_resident, for_init=False, warps=0):
+    def _bucket(self, ids, cand, want_resident, for_init=False, warps=0, cluster=0):
         b = _Bucket()
         order = ids[np.argsort(-cand[ids], kind="stable")]
         b.n = len(order)
         b.max_cols = int(cand[ids].max())
-        b.plan = self._make_plan(b.max_cols, b.n, want_resident, for_init, warps)
+        b.plan = self._make_plan(b.max_cols, b.n, want_resident, for_init, warps, cluster)
         b.order = torch.from_numpy(order.astype(np.int32)).to(self.device)
         b.ws = torch.empty(int(b.plan.ws_bytes), dtype=torch.uint8, device=self.device)
         b.stream = None
@@ -137,6 +141,19 @@ class ShardEngine(object):
         if self.init_bucket is not None:
             self.init_bucket.stream = torch.cuda.Stream(device=self.device)
 
+    def _cluster_share_cap(self, cl):
+        """Largest per-CTA column share a resident cluster plan accepts (pure host arithmetic)."""
+        lo, hi = 8, 4096
+        while lo < hi:
+            mid = (lo + hi + 1) // 2 // 8 * 8
+            if mid <= lo:
+                break
+            if self._make_plan(mid * cl, 1, -1, cluster=cl).resident_cols > 0:
+                lo = mid
+            else:
+                hi = mid - 8
+        return lo
+
     def _plan_buckets(self):
         n, L, r = self.n, self.lengths, self.prm.downsample_rate
         self.buckets = []
@@ -147,8 +164,10 @@ class ShardEngine(object):
         self.init_bucket = self._bucket(np.arange(n), L, 0, for_init=True)
         # baseline selection: bucket by the number of candidate columns, ceil(L / rate)
         cand = (L + r - 1) // r
-        if self.force_streamed:
-            self.buckets.append(self._bucket(np.arange(n), cand, 0))
+        if self.force_streamed or self.force_cluster:
+            # testing aids: everything through the streamed tier and / or through clusters of a given size
+            self.buckets.append(self._bucket(np.arange(n), cand, 0 if self.force_streamed else -1,
+                                             cluster=self.force_cluster if self.p <= 12 else 0))
             return
         left = np.ones(n, dtype=bool)
         prev = 0
@@ -162,9 +181,17 @@ class ShardEngine(object):
                     self.buckets.append(self._bucket(sel, cand, tier, warps=warps))
                     left[sel] = False
                 prev = max(prev, tier)
+            # longer genes: one thread-block cluster per gene, columns split over its CTAs' shared memory
+            for cl in (self.clusters if self.use_clusters else ()):
+                cap = cl * self._cluster_share_cap(cl)
+                sel = np.flatnonzero(left & (cand <= cap))
+                if len(sel):
+                    self.buckets.append(self._bucket(sel, cand, -1, cluster=cl))
+                    left[sel] = False
             rest = np.flatnonzero(left)
             if len(rest):
-                self.buckets.append(self._bucket(rest, cand, 0))
+                # beyond the largest cluster's shared memory: streamed from per-CTA slabs, still split over a cluster
+                self.buckets.append(self._bucket(rest, cand, 0, cluster=(self.clusters[-1] if self.use_clusters else 0)))
             return
         for tier in RESIDENT_TIERS:
             plan = self._make_plan(tier, 1, tier)

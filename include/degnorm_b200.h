@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 2
+#define DN_ABI_VERSION 3
 #define DN_MAX_BINS 64      /* baseline-selection bins held in the fused kernel (reference default: 20) */
 #define DN_MAX_SAMPLES 256  /* p supported by the fused kernels (one thread per sample in the n x p steps) */
 #define DN_NCOUNTERS 8      /* int32 counters per gene, see dn_counter */
@@ -86,6 +86,8 @@ typedef struct dn_plan {
     int32_t resident_cols;  /* columns of x and lambda held in shared memory (0: none)          */
     int32_t chunk_cols;     /* columns per Gram tile pass                                       */
     int32_t smem_bytes;     /* dynamic shared memory per CTA                                    */
+    int32_t cluster;        /* CTAs per gene: 1, or a thread-block cluster of 2/4/8/16 (small-p path)  */
+    int32_t reserved;
     int64_t ws_cols;        /* columns of per-CTA global workspace (0: none needed)             */
     int64_t ws_bytes;       /* total workspace bytes this launch needs (all CTAs + queue)       */
 } dn_plan;
@@ -101,11 +103,13 @@ int dn_device_info(int32_t *sm_count, int32_t *max_smem_optin, int32_t *cc);
  * for downsample_rate 1, ceil(L/rate) otherwise).  want_resident: shared-memory column capacity wanted
  * (0 forces the streamed path, -1 = as many as fit).  for_init=1 sizes the workspace for dn_init_ratio_svd.
  * warps: warps per CTA on the small-p path (1, 2, 4, 8, 16; 0 = chosen from the tier), ignored elsewhere.
+ * cluster: CTAs that share one gene on the small-p path (0/1: none; 2, 4, 8, 16: a thread-block cluster whose
+ * CTAs each hold ceil(max_cols/cluster) columns and exchange the partial Gram through distributed shared memory).
  * On the small-p path (p <= 12, for_init = 0) a bucket is wholly resident (max_cols fit in shared memory) or
  * wholly streamed; on the tiled path residency is decided per gene.
  * Pure host arithmetic (no device call): sm_count / max_smem come from dn_device_info. */
 int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t want_resident, int32_t for_init,
-                 int32_t warps, int32_t sm_count, int32_t max_smem_optin, dn_plan *plan);
+                 int32_t warps, int32_t cluster, int32_t sm_count, int32_t max_smem_optin, dn_plan *plan);
 
 /* Replaces run_ratio_svd_serial / ratio_svd over all genes + the two row sums run() takes of it
  * (nmf.py:109-140, 521-527): est_rowsum[g,i] = sum_j max(R1(F_g)_ij, F_g[i,j]), cov_rowsum[g,i] = sum_j F_g[i,j]

@@ -129,6 +129,38 @@ def test_streamed_tier_equals_resident_tier():
     np.testing.assert_allclose(a["est"], b["est"], rtol=1e-10, atol=1e-10)
 
 
+@pytest.mark.parametrize("p,cluster,streamed", [(4, 2, False), (12, 4, False), (12, 8, True), (7, 16, False)])
+def test_cluster_path_equals_single_cta_path(p, cluster, streamed):
+    """The same genes with one CTA per gene and with a thread-block cluster per gene (columns split over the CTAs'
+    shared memory or slabs, partial Gram exchanged through distributed shared memory): identical decisions and
+    call sequences, DI equal to rounding."""
+    import torch
+    from degnorm_b200.engine import Params, ShardEngine
+    from degnorm_b200.packing import pack_coverage
+    from degnorm_b200.synth import synth_numpy
+    lengths = np.array([300, 520, 810, 1250, 260, 640, 2900, 410, 95, 1700])
+    mats, reads = synth_numpy(len(lengths), p, 100 + p, lengths=lengths, jitter=1e-6)
+    prm = Params(degnorm_iter=2, nmf_iter=40)
+    flat, off = pack_coverage(mats, p)
+    outs = []
+    for cl in (0, cluster):
+        eng = ShardEngine(prm, p, "cuda:0")
+        eng.force_cluster = cl
+        eng.force_streamed = streamed and cl > 0
+        eng.load(flat.cuda(), off, torch.from_numpy(reads).cuda())
+        if cl:
+            assert all(int(b.plan.cluster) == cl for b in eng.buckets)
+        o = eng.run(None, want_estimates=True)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items() if v is not None})
+    a, b = outs
+    np.testing.assert_array_equal(a["ran"], b["ran"])
+    np.testing.assert_array_equal(a["counters"][:, :, :4], b["counters"][:, :, :4])
+    np.testing.assert_array_equal(a["counters"][:, :, 5:7], b["counters"][:, :, 5:7])
+    np.testing.assert_allclose(a["rho"], b["rho"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(a["est"], b["est"], rtol=1e-9, atol=1e-9)
+
+
 def test_init_pass_matches_kat():
     """ratio_svd known-answer vector (produced by the reference)."""
     import os

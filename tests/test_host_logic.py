@@ -76,28 +76,28 @@ def test_plan_is_pure_host_arithmetic():
     plan = _lib.DnPlan()
     # small-p path (p <= 12): tile 0, warps from the tier, a bucket is wholly resident or wholly streamed
     prm = Params(downsample_rate=20).to_c(12)
-    assert lib.dn_make_plan(C.byref(prm), 64, 100000, 64, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(prm), 64, 100000, 64, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 0 and plan.threads == 32 and plan.resident_cols == 64 and plan.ws_cols == 0
     assert plan.smem_bytes < 24 * 1024 and plan.ctas > 8 * 148
-    assert lib.dn_make_plan(C.byref(prm), 400, 1000, 448, 0, 4, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(prm), 400, 1000, 448, 0, 4, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.threads == 128 and plan.resident_cols == 400 and 2 * (plan.smem_bytes + 1024) <= 228 * 1024
-    assert lib.dn_make_plan(C.byref(prm), 100000, 1000, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(prm), 100000, 1000, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 0 and plan.resident_cols == 0 and plan.ws_cols >= 100000 and plan.threads == 256
-    assert lib.dn_make_plan(C.byref(prm), 64, 10, 64, 0, 3, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
+    assert lib.dn_make_plan(C.byref(prm), 64, 10, 64, 0, 3, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
     # the init pass and p > 12 use the tiled kernel
-    assert lib.dn_make_plan(C.byref(prm), 5000, 1000, 0, 1, 0, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(prm), 5000, 1000, 0, 1, 0, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 4 and plan.threads == 256
     prm48 = Params().to_c(48)
-    assert lib.dn_make_plan(C.byref(prm48), 100000, 1000, -1, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(prm48), 100000, 1000, -1, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 4 and 0 < plan.resident_cols < 100000 and plan.ws_cols >= 100000
     bad = Params().to_c(1)
-    assert lib.dn_make_plan(C.byref(bad), 128, 10, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
+    assert lib.dn_make_plan(C.byref(bad), 128, 10, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
     assert b"2 samples" in lib.dn_last_error()
     p200 = Params().to_c(200)
-    assert lib.dn_make_plan(C.byref(p200), 3000, 100, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(p200), 3000, 100, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 8 and plan.resident_cols == 0 and plan.ws_bytes > 0
     big = Params().to_c(5000)
-    assert lib.dn_make_plan(C.byref(big), 128, 10, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_UNSUPPORTED
+    assert lib.dn_make_plan(C.byref(big), 128, 10, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_UNSUPPORTED
 
 
 def test_no_cpu_fallback():
