@@ -99,6 +99,12 @@ def adapt(comm):
         return SoloComm()
     if isinstance(comm, (SoloComm, MPIComm, TorchComm)):
         return comm
+    try:
+        import torch.distributed as dist
+        if isinstance(comm, dist.ProcessGroup):        # (it also has send / recv methods: test it first)
+            return TorchComm(comm)
+    except ImportError:
+        pass
     if hasattr(comm, "send") and hasattr(comm, "recv"):
         return MPIComm(comm)
-    return TorchComm(comm)
+    raise TypeError("comm must be an mpi4py-style communicator, a torch.distributed process group or None")

@@ -143,6 +143,9 @@ def _gpu_worker(rank, world, port, q):
         cov = OrderedDict(("g%d" % i, m) for i, m in enumerate(mats))
         out = run_gene_nmfoa_mpi(dist.group.WORLD, cov if rank == 0 else OrderedDict(), reads, device="cuda:0", **kw)
         q.put((rank, None if out is None else {k: (v if k != "estimates" else list(v.values())) for k, v in out.items()}))
+    except Exception as exc:                                   # surface the failure instead of a silent time-out
+        import traceback
+        q.put((rank, "ERROR: %s\n%s" % (exc, traceback.format_exc())))
     finally:
         dist.destroy_process_group()
 
@@ -162,13 +165,32 @@ def test_two_processes_on_one_gpu_equal_single_process():
     np.testing.assert_array_equal(solo["rho"], single.rho)
     np.testing.assert_array_equal(solo["ran_baseline_selection"], single.ran_baseline_selection)
     assert list(solo["estimates"].keys()) == list(cov.keys())
+
+    class OneRankMPI(object):                     # the lowercase mpi4py object API degnorm_mpi passes (COMM_WORLD)
+        rank, size = 0, 1
+
+        def send(self, obj, dest, tag=0):
+            raise AssertionError("nothing to send with one rank")
+
+        def recv(self, source, tag=0):
+            raise AssertionError("nothing to receive with one rank")
+
+        def allreduce(self, x):
+            return x
+
+        def Barrier(self):
+            pass
+    via_mpi = run_gene_nmfoa_mpi(OneRankMPI(), cov, reads, **kw)
+    np.testing.assert_array_equal(via_mpi["rho"], single.rho)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
     for pr in procs:
         pr.start()
-    got = dict(q.get(timeout=600) for _ in procs)
+    got = dict(q.get(timeout=240) for _ in procs)
+    for v in got.values():
+        assert not isinstance(v, str), v
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
