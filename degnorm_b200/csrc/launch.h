@@ -66,7 +66,7 @@ constexpr int SMALL_CLMAX = 16;       // largest thread-block cluster per gene (
 constexpr int SMALL_CLU_WARPS = 8;    // warps per CTA of the cluster kernels
 
 struct SmallCarve {
-    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, lw, xbuf, X, M, resb, tb, total;   // offsets in doubles
+    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, lw, xbuf, stage, X, M, resb, tb, total;   // offsets in doubles
 };
 
 __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_cols, bool clu = false) {
@@ -84,6 +84,7 @@ __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_co
     c.lw = o;    o += DN_MAX_BINS / 2;          // per-bin local widths (ints)
     c.xbuf = o;  o += clu ? 2ll * SMALL_CLMAX * SMALL_GPART : 0;   // cluster exchange slots
     const long long cs = small_cs(P);
+    c.stage = o; o += resident_cols > 0 ? 0 : (long long)nw * 32 * cs;   // streamed tier: per-warp stage of M
     c.X = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
     c.M = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
     c.resb = o;  o += resident_cols > 0 ? resident_cols : 0;

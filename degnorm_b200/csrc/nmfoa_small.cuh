@@ -60,6 +60,7 @@ struct SGene {
     int eig_steps, eig_fallbacks, gpar;
     double *B0;
     // cluster state (CLU kernels; a lone CTA is rank 0 of 1): n0 / n_cur are this CTA's columns, n0g / n_curg the gene's
+    double *stage;      // streamed tier: one 32-column stage of M per warp
     double *xbuf;       // exchange slots: 2 alternating sets of SMALL_CLMAX x SMALL_GPART doubles (peers write here)
     int *lw;            // this CTA's width of every original bin
     int crank, csize, xpar, n0g, n_curg, goff;
@@ -161,7 +162,7 @@ __device__ __forceinline__ void block_sum_vec(double (&x)[NV], double *part, dou
 // ---- one pass: (optional multiplier update of this warp's columns) + Gram of M -----------------------------------
 // UPDATE=false: G = M M^T with M = x (first rank-one fit, nmf.py:88).
 // UPDATE=true : lambda <- max(0, lambda - c (K E - x)), M = x + lambda, G = M M^T (nmf.py:93-98); K E = v (v.M_old).
-template <int P, int NW, bool UPDATE, bool CLU>
+template <int P, int NW, bool UPDATE, bool CLU, bool RES>
 __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const double (&v)[P]) {
     using Cfg = SmallCfg<P>;
     constexpr int TC = Cfg::TC, KS = Cfg::KS, NTP = Cfg::NTP, NTILE = Cfg::NTILE, CS = P + 2, NT = NW * 32;
@@ -177,6 +178,68 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
     // this warp's contiguous column range (whole 32-column blocks)
     const int per_warp = ((n + 31) / 32 + NW - 1) / NW * 32;
     const int c_lo = min(warp * per_warp, n), c_hi = min(c_lo + per_warp, n);
+    const int oR = g.tpack & 15, oA = (g.tpack >> 4) & 15, oB = (g.tpack >> 8) & 15;
+    const int ks = lane / NTP;
+    if constexpr (!RES) {
+        // Streamed tier: x and M live in the CTA's global slab.  Per 32-column block: phase A from registers
+        // (the next block's x and M are already in flight), new M to the slab AND to a warp-private shared
+        // stage, phase B out of the stage -- global traffic per column is read x, read M, write M and nothing else.
+        double *stage = g.stage + warp * (32 * CS);
+        double x[P], m[P];
+        int col = c_lo + lane;
+        if (col < c_hi) {
+            load_col<P>(g.M + (long long)col * CS, m);
+            if constexpr (UPDATE) load_col<P>(g.X + (long long)col * CS, x);
+        }
+        for (int b0 = c_lo; b0 < c_hi; b0 += 32) {
+            double xn[P], mn[P];
+            const int coln = col + 32;
+            if (coln < c_hi) {
+                load_col<P>(g.M + (long long)coln * CS, mn);
+                if constexpr (UPDATE) load_col<P>(g.X + (long long)coln * CS, xn);
+            }
+            if (col < c_hi) {
+                if constexpr (UPDATE) {
+                    const double t = dot_v<P>(v, m);
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        const double res = fma(v[i], t, -x[i]);
+                        const double w = fma(-c, res, m[i] - x[i]);
+                        m[i] = fma(0.5, w + fabs(w), x[i]);
+                    }
+                    double2 *mq = reinterpret_cast<double2 *>(g.M + (long long)col * CS);
+#pragma unroll
+                    for (int i = 0; i < P / 2; ++i) mq[i] = make_double2(m[2 * i], m[2 * i + 1]);
+                }
+                double2 *sq = reinterpret_cast<double2 *>(stage + lane * CS);
+#pragma unroll
+                for (int i = 0; i < P / 2; ++i) sq[i] = make_double2(m[2 * i], m[2 * i + 1]);
+            }
+            __syncwarp();
+            if (g.tpack >= 0) {
+                const int nb = min(32, c_hi - b0);
+                const double *mc = stage + ks * CS;
+#pragma unroll 4
+                for (int j = ks; j < nb; j += KS, mc += KS * CS) {
+                    const double2 ar = *reinterpret_cast<const double2 *>(mc + oR);
+                    const double2 ua = *reinterpret_cast<const double2 *>(mc + oA);
+                    acc[0][0] = fma(ar.x, ua.x, acc[0][0]);
+                    acc[0][1] = fma(ar.x, ua.y, acc[0][1]);
+                    acc[1][0] = fma(ar.y, ua.x, acc[1][0]);
+                    acc[1][1] = fma(ar.y, ua.y, acc[1][1]);
+                    if constexpr (TC == 3) {
+                        const double ub = mc[oB];
+                        acc[0][2] = fma(ar.x, ub, acc[0][2]);
+                        acc[1][2] = fma(ar.y, ub, acc[1][2]);
+                    }
+                }
+            }
+            __syncwarp();
+            col = coln;
+#pragma unroll
+            for (int i = 0; i < P; ++i) { m[i] = mn[i]; if constexpr (UPDATE) x[i] = xn[i]; }
+        }
+    } else {
     if constexpr (UPDATE) {
         // phase A: one lane per column; columns are independent, two in flight per lane
 #pragma unroll 2
@@ -200,8 +263,6 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
     }
     if (g.tpack >= 0) {
         // phase B: this lane's Gram tile over its k-slice of the warp's columns
-        const int ks = lane / NTP;
-        const int oR = g.tpack & 15, oA = (g.tpack >> 4) & 15, oB = (g.tpack >> 8) & 15;
         const double *mc = g.M + (c_lo + ks) * CS;
 #pragma unroll 4
         for (int col = c_lo + ks; col < c_hi; col += KS, mc += KS * CS) {
@@ -217,6 +278,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
                 acc[1][2] = fma(ar.y, ub, acc[1][2]);
             }
         }
+    }
     }
     // k-slice reduction (lane = ks * NTP + tile)
 #pragma unroll
@@ -457,7 +519,7 @@ __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P],
 }
 
 // nmf() on the current columns [0, n_cur) (nmf.py:78-107).  Leaves v, K, tmp = rs(KE), rsF, rsC, resb, tb.
-template <int P, int NW, bool CLU>
+template <int P, int NW, bool CLU, bool RES>
 __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_res, double *e_first_g) {
     constexpr int NT = NW * 32, CS = P + 2;
     const int tid = threadIdx.x;
@@ -473,11 +535,11 @@ __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_re
     for (int k = 0; k < P; ++k) v[k] = 0.0;
     double inv_lam = 1.0;
     int hint = 0;
-    gram_small<P, NW, false, CLU>(a, g, v);
+    gram_small<P, NW, false, CLU, RES>(a, g, v);
     eig_small<P, NW>(a, g, v, true, inv_lam, hint);
     const int T = a.nmf_iter;
     for (int it = 0; it < T; ++it) {
-        gram_small<P, NW, true, CLU>(a, g, v);
+        gram_small<P, NW, true, CLU, RES>(a, g, v);
         eig_small<P, NW>(a, g, v, false, inv_lam, hint);
     }
     final_pass_small<P, NW, CLU>(a, g, v, first, want_res, e_first_g);
@@ -506,6 +568,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
     g.tab = reinterpret_cast<int *>(smem + cv.tab);
     g.lw = reinterpret_cast<int *>(smem + cv.lw);
     g.xbuf = smem + cv.xbuf;
+    g.stage = smem + cv.stage;
     g.crank = 0; g.csize = 1; g.xpar = 0;
     if constexpr (CLU) {
         cg::cluster_group cl = cg::this_cluster();
@@ -691,7 +754,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 bool first = true, in_loop = false;
                 double rmax = 0.0;
                 for (;;) {
-                    run_nmf_small<P, NW, CLU>(a, g, first, true, (first && store_e) ? a.e_first + o0 : nullptr);
+                    run_nmf_small<P, NW, CLU, RES>(a, g, first, true, (first && store_e) ? a.e_first + o0 : nullptr);
                     nmf_calls += 1; sum_cols += g.n_curg;
                     if (first) {
                         if (tid < P) {
