@@ -95,7 +95,9 @@ __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_co
 
 // per-CTA global slab of the small path (doubles): eigen fallback scratch + streamed column storage
 __host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols) {
-    const long long d = 2ll * P * P + (2ll * small_cs(P) + 2) * ws_cols;
+    // x and M blocked row-major (P doubles per column, whole 32-column blocks), residuals and t one double each
+    const long long cols = (ws_cols + 31) / 32 * 32;
+    const long long d = 2ll * P * P + (2ll * P + 2) * cols;
     return (d + 31) / 32 * 32;
 }
 

@@ -91,6 +91,32 @@ __device__ __forceinline__ void load_col(const double *base, double (&x)[P]) {
     }
 }
 
+// Column accessors.  Resident tiers (RES): shared memory, column-major, stride P+2 doubles.  Streamed tier: the
+// CTA's global slab, "blocked row-major": 32-column blocks, inside a block row i holds its 32 columns contiguously,
+// so a warp reading one column per lane issues fully coalesced 256-byte requests (no padding bytes either).
+template <int P, bool RES>
+__device__ __forceinline__ void ld_col(const double *base, int col, double (&x)[P]) {
+    if constexpr (RES) {
+        load_col<P>(base + col * (P + 2), x);
+    } else {
+        const double *q = base + (long long)(col >> 5) * (32 * P) + (col & 31);
+#pragma unroll
+        for (int i = 0; i < P; ++i) x[i] = q[i * 32];
+    }
+}
+template <int P, bool RES>
+__device__ __forceinline__ void st_col(double *base, int col, const double (&x)[P]) {
+    if constexpr (RES) {
+        double2 *q = reinterpret_cast<double2 *>(base + col * (P + 2));
+#pragma unroll
+        for (int i = 0; i < P / 2; ++i) q[i] = make_double2(x[2 * i], x[2 * i + 1]);
+    } else {
+        double *q = base + (long long)(col >> 5) * (32 * P) + (col & 31);
+#pragma unroll
+        for (int i = 0; i < P; ++i) q[i * 32] = x[i];
+    }
+}
+
 template <int P>
 __device__ __forceinline__ double dot_v(const double (&v)[P], const double (&m)[P]) {
     double t0 = 0.0, t1 = 0.0;
@@ -188,15 +214,15 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
         double x[P], m[P];
         int col = c_lo + lane;
         if (col < c_hi) {
-            load_col<P>(g.M + (long long)col * CS, m);
-            if constexpr (UPDATE) load_col<P>(g.X + (long long)col * CS, x);
+            ld_col<P, false>(g.M, col, m);
+            if constexpr (UPDATE) ld_col<P, false>(g.X, col, x);
         }
         for (int b0 = c_lo; b0 < c_hi; b0 += 32) {
             double xn[P], mn[P];
             const int coln = col + 32;
             if (coln < c_hi) {
-                load_col<P>(g.M + (long long)coln * CS, mn);
-                if constexpr (UPDATE) load_col<P>(g.X + (long long)coln * CS, xn);
+                ld_col<P, false>(g.M, coln, mn);
+                if constexpr (UPDATE) ld_col<P, false>(g.X, coln, xn);
             }
             if (col < c_hi) {
                 if constexpr (UPDATE) {
@@ -207,9 +233,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
                         const double w = fma(-c, res, m[i] - x[i]);
                         m[i] = fma(0.5, w + fabs(w), x[i]);
                     }
-                    double2 *mq = reinterpret_cast<double2 *>(g.M + (long long)col * CS);
-#pragma unroll
-                    for (int i = 0; i < P / 2; ++i) mq[i] = make_double2(m[2 * i], m[2 * i + 1]);
+                    st_col<P, false>(g.M, col, m);
                 }
                 double2 *sq = reinterpret_cast<double2 *>(stage + lane * CS);
 #pragma unroll
@@ -464,7 +488,7 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
 }
 
 // ---- final pass of an nmf() call (see final_pass in nmfoa_tiled.cu for what each sum is) ----------------------
-template <int P, int NW, bool CLU>
+template <int P, int NW, bool CLU, bool RES>
 __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P], bool first, bool want_res,
                                  double *e_first_g) {
     constexpr int NT = NW * 32, CS = P + 2, NV = 2 + 2 * P;
@@ -475,8 +499,8 @@ __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P],
     for (int k = 0; k < NV; ++k) acc[k] = 0.0;
     for (int col = tid; col < n; col += NT) {
         double x[P], m[P];
-        load_col<P>(g.X + col * CS, x);
-        load_col<P>(g.M + col * CS, m);
+        ld_col<P, RES>(g.X, col, x);
+        ld_col<P, RES>(g.M, col, m);
         const double t = dot_v<P>(v, m);
         g.tb[col] = t;
         acc[0] += t;
@@ -526,7 +550,8 @@ __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_re
     {   // lambda = 0: M = x
         const double2 *src = reinterpret_cast<const double2 *>(g.X);
         double2 *dst = reinterpret_cast<double2 *>(g.M);
-        const int n2 = g.n_cur * (CS / 2);
+        // (flat copy of the storage that holds the first n_cur columns, whole blocks in the streamed layout)
+        const int n2 = RES ? g.n_cur * (CS / 2) : (g.n_cur + 31) / 32 * (32 * P / 2);
         for (int e = tid; e < n2; e += NT) dst[e] = src[e];
     }
     bsync<NW>();
@@ -542,7 +567,7 @@ __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_re
         gram_small<P, NW, true, CLU, RES>(a, g, v);
         eig_small<P, NW>(a, g, v, false, inv_lam, hint);
     }
-    final_pass_small<P, NW, CLU>(a, g, v, first, want_res, e_first_g);
+    final_pass_small<P, NW, CLU, RES>(a, g, v, first, want_res, e_first_g);
 }
 
 template <int P, int NW, bool RES, bool CLU>
@@ -582,9 +607,10 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
         g.X = smem + cv.X; g.M = smem + cv.M; g.resb = smem + cv.resb; g.tb = smem + cv.tb;
     } else {
         g.X = slab + 2 * P * P;
-        g.M = g.X + (long long)CS * a.ws_ld;
-        g.resb = g.M + (long long)CS * a.ws_ld;
-        g.tb = g.resb + a.ws_ld;
+        const long long wcols = (a.ws_ld + 31) / 32 * 32;           // whole 32-column blocks (blocked row-major)
+        g.M = g.X + (long long)P * wcols;
+        g.resb = g.M + (long long)P * wcols;
+        g.tb = g.resb + wcols;
     }
     {   // this lane's Gram tile; table of all tiles for the cross-warp sum
         const int t = lane % Cfg::NTP;
@@ -700,9 +726,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 }
                 if (keep) {
                     const int dst = pre + __popc(bal & ((1u << lane) - 1u));
-                    double2 *xq = reinterpret_cast<double2 *>(g.X + (long long)dst * CS);
-#pragma unroll
-                    for (int i = 0; i < P / 2; ++i) xq[i] = make_double2(xv[2 * i], xv[2 * i + 1]);
+                    st_col<P, RES>(g.X, dst, xv);
                 }
                 running += tot;
                 if constexpr (NW > 1) __syncthreads();
@@ -737,7 +761,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                 for (int i = 0; i < P; ++i) rs[i] = 0.0;
                 for (int col = tid; col < g.n0; col += NT) {
                     double x[P];
-                    load_col<P>(g.X + col * CS, x);
+                    ld_col<P, RES>(g.X, col, x);
 #pragma unroll
                     for (int i = 0; i < P; ++i) rs[i] += x[i];
                 }
@@ -825,15 +849,18 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                         const int a0 = lstart(g, kd);
                         const int wl = g.lw[bd];
                         const int tail = g.n_cur - a0 - wl;
-                        const double2 *xs = reinterpret_cast<const double2 *>(g.X + (long long)a0 * CS);
-                        double2 *ms = reinterpret_cast<double2 *>(g.M + (long long)a0 * CS);
-                        const int h = CS / 2;
                         bsync<NW>();
-                        for (int e = tid; e < (tail + wl) * h; e += NT) ms[e] = xs[e];
+                        for (int c = tid; c < tail + wl; c += NT) {
+                            double x[P];
+                            ld_col<P, RES>(g.X, a0 + c, x);
+                            st_col<P, RES>(g.M, a0 + c, x);
+                        }
                         bsync<NW>();
-                        double2 *xd = reinterpret_cast<double2 *>(g.X + (long long)a0 * CS);
-                        for (int e = tid; e < tail * h; e += NT) xd[e] = ms[wl * h + e];
-                        for (int e = tid; e < wl * h; e += NT) xd[tail * h + e] = ms[e];
+                        for (int c = tid; c < tail + wl; c += NT) {
+                            double x[P];
+                            ld_col<P, RES>(g.M, a0 + (c < tail ? wl + c : c - tail), x);
+                            st_col<P, RES>(g.X, a0 + c, x);
+                        }
                         if (tid == 0)
                             for (int k = kd; k < g.nalive - 1; ++k) g.alive[k] = g.alive[k + 1];
                         g.n_cur -= wl;
@@ -853,7 +880,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                         double s = 0.0;
                         for (int j = tid; j < g.n0; j += NT) {
                             double x[P];
-                            load_col<P>(g.X + j * CS, x);
+                            ld_col<P, RES>(g.X, j, x);
                             double e = -1.0e300;
 #pragma unroll
                             for (int i = 0; i < P; ++i)
