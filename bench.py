@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial-buckets", action="store_true", help="tuning: run the tiers one after another")
+    ap.add_argument("--force-cluster", type=int, default=0, help="tuning: every gene through clusters of this size")
+    ap.add_argument("--force-streamed", action="store_true", help="tuning: every gene through the streamed tier")
     ap.add_argument("--tiers", default="", help="small-p tiers as cols:warps,... (tuning)")
     return ap.parse_args()
 
@@ -239,7 +241,8 @@ def main():
     prm = Params(**kw)
     ds = draw_offsets(n, prm)
     tiers = tuple(tuple(int(x) for x in t.split(":")) for t in args.tiers.split(",")) if args.tiers else None
-    eng = ShardEngine(prm, p, dev, group=group, small_tiers=tiers)
+    eng = ShardEngine(prm, p, dev, group=group, small_tiers=tiers, force_streamed=args.force_streamed)
+    eng.force_cluster = args.force_cluster
     eng.load(cov, off, reads)
     eng.record_events = True
     eng.serial_buckets = args.serial_buckets

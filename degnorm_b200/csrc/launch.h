@@ -64,9 +64,10 @@ constexpr int SMALL_GPART = 96;       // doubles per warp of partial Gram / redu
 constexpr int SMALL_MAX_WARPS = 16;
 constexpr int SMALL_CLMAX = 16;       // largest thread-block cluster per gene (non-portable size)
 constexpr int SMALL_CLU_WARPS = 8;    // warps per CTA of the cluster kernels
+constexpr int SMALL_RING = 3;         // streamed tier: cp.async ring stages per warp (RING - 1 blocks in flight)
 
 struct SmallCarve {
-    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, lw, xbuf, stage, X, M, resb, tb, total;   // offsets in doubles
+    long long small, red, binm, alive, ibuf, G, vx, gpart, tab, lw, xbuf, stage, ring, X, M, resb, tb, total;   // offsets in doubles
 };
 
 __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_cols, bool clu = false) {
@@ -85,6 +86,7 @@ __host__ __device__ inline SmallCarve small_carve(int P, int nw, int resident_co
     c.xbuf = o;  o += clu ? 2ll * SMALL_CLMAX * SMALL_GPART : 0;   // cluster exchange slots
     const long long cs = small_cs(P);
     c.stage = o; o += resident_cols > 0 ? 0 : (long long)nw * 32 * cs;   // streamed tier: per-warp stage of M
+    c.ring = o;  o += resident_cols > 0 ? 0 : (long long)nw * SMALL_RING * 2 * 32 * P;   // and cp.async ring
     c.X = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
     c.M = o;     o += resident_cols > 0 ? cs * resident_cols : 0;
     c.resb = o;  o += resident_cols > 0 ? resident_cols : 0;

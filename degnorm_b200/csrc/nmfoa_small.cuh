@@ -61,6 +61,7 @@ struct SGene {
     double *B0;
     // cluster state (CLU kernels; a lone CTA is rank 0 of 1): n0 / n_cur are this CTA's columns, n0g / n_curg the gene's
     double *stage;      // streamed tier: one 32-column stage of M per warp
+    double *ring;       // streamed tier: per-warp cp.async ring of x / M blocks
     double *xbuf;       // exchange slots: 2 alternating sets of SMALL_CLMAX x SMALL_GPART doubles (peers write here)
     int *lw;            // this CTA's width of every original bin
     int crank, csize, xpar, n0g, n_curg, goff;
@@ -78,6 +79,17 @@ __device__ __forceinline__ void tile_of(int t, int &r0, int &c0, bool &ok) {
                 if (idx == t) { r0 = 2 * rb; c0 = cb * TC; ok = true; }
                 ++idx;
             }
+}
+
+// ---- cp.async (LDGSTS) helpers: 16-byte global -> shared copies that bypass registers and L1 --------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
 template <int P>
@@ -207,25 +219,46 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
     const int oR = g.tpack & 15, oA = (g.tpack >> 4) & 15, oB = (g.tpack >> 8) & 15;
     const int ks = lane / NTP;
     if constexpr (!RES) {
-        // Streamed tier: x and M live in the CTA's global slab.  Per 32-column block: phase A from registers
-        // (the next block's x and M are already in flight), new M to the slab AND to a warp-private shared
-        // stage, phase B out of the stage -- global traffic per column is read x, read M, write M and nothing else.
+        // Streamed tier: x and M live in the CTA's global slab (blocked row-major).  Each warp streams its 32-column
+        // blocks through a private shared-memory ring filled by cp.async (SMALL_RING stages, so SMALL_RING - 1
+        // blocks = 6 KB per array pair are in flight per warp while it computes): phase A reads the landed block,
+        // writes the new M to the slab (coalesced) and to a column-major stage, phase B runs out of the stage.
+        // Global traffic per column-iteration is exactly read x, read M, write M.
+        constexpr int BLK = 32 * P;                              // doubles per block per array
         double *stage = g.stage + warp * (32 * CS);
-        double x[P], m[P];
-        int col = c_lo + lane;
-        if (col < c_hi) {
-            ld_col<P, false>(g.M, col, m);
-            if constexpr (UPDATE) ld_col<P, false>(g.X, col, x);
-        }
-        for (int b0 = c_lo; b0 < c_hi; b0 += 32) {
-            double xn[P], mn[P];
-            const int coln = col + 32;
-            if (coln < c_hi) {
-                ld_col<P, false>(g.M, coln, mn);
-                if constexpr (UPDATE) ld_col<P, false>(g.X, coln, xn);
-            }
-            if (col < c_hi) {
+        double *ring = g.ring + warp * (SMALL_RING * 2 * BLK);
+        const int b_lo = c_lo >> 5, b_hi = (c_hi + 31) >> 5;
+        auto issue = [&](int blk) {
+            if (blk < b_hi) {
+                double *dst = ring + (blk % SMALL_RING) * (2 * BLK);
+                const double *srcM = g.M + (long long)blk * BLK;
+#pragma unroll
+                for (int c = 0; c < BLK / 64; ++c) cp_async16(dst + (c * 32 + lane) * 2, srcM + (c * 32 + lane) * 2);
                 if constexpr (UPDATE) {
+                    const double *srcX = g.X + (long long)blk * BLK;
+#pragma unroll
+                    for (int c = 0; c < BLK / 64; ++c)
+                        cp_async16(dst + BLK + (c * 32 + lane) * 2, srcX + (c * 32 + lane) * 2);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int q = 0; q < SMALL_RING - 1; ++q) issue(b_lo + q);
+        for (int blk = b_lo; blk < b_hi; ++blk) {
+            issue(blk + SMALL_RING - 1);
+            cp_async_wait<SMALL_RING - 1>();
+            __syncwarp();
+            const double *rm = ring + (blk % SMALL_RING) * (2 * BLK) + lane;
+            const int col = blk * 32 + lane;
+            if (col < c_hi) {
+                double m[P];
+#pragma unroll
+                for (int i = 0; i < P; ++i) m[i] = rm[i * 32];
+                if constexpr (UPDATE) {
+                    double x[P];
+#pragma unroll
+                    for (int i = 0; i < P; ++i) x[i] = rm[BLK + i * 32];
                     const double t = dot_v<P>(v, m);
 #pragma unroll
                     for (int i = 0; i < P; ++i) {
@@ -241,7 +274,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
             }
             __syncwarp();
             if (g.tpack >= 0) {
-                const int nb = min(32, c_hi - b0);
+                const int nb = min(32, c_hi - blk * 32);
                 const double *mc = stage + ks * CS;
 #pragma unroll 4
                 for (int j = ks; j < nb; j += KS, mc += KS * CS) {
@@ -259,10 +292,8 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
                 }
             }
             __syncwarp();
-            col = coln;
-#pragma unroll
-            for (int i = 0; i < P; ++i) { m[i] = mn[i]; if constexpr (UPDATE) x[i] = xn[i]; }
         }
+        cp_async_wait<0>();
     } else {
     if constexpr (UPDATE) {
         // phase A: one lane per column; columns are independent, two in flight per lane
@@ -594,6 +625,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
     g.lw = reinterpret_cast<int *>(smem + cv.lw);
     g.xbuf = smem + cv.xbuf;
     g.stage = smem + cv.stage;
+    g.ring = smem + cv.ring;
     g.crank = 0; g.csize = 1; g.xpar = 0;
     if constexpr (CLU) {
         cg::cluster_group cl = cg::this_cluster();
