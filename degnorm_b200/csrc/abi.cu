@@ -304,8 +304,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         const long long per_col = 8ll * (2 * small_cs(P) + 2);
         long long share = (max_cols + cluster - 1) / cluster;
         share = (share + 7) / 8 * 8;
-        const long long fixed_b = small_carve(P, SMALL_CLU_WARPS, 0, true).total * 8;
-        const bool res = want_resident != 0 && fixed_b + share * per_col <= max_smem_optin;
+        const bool res = want_resident != 0 && small_carve(P, SMALL_CLU_WARPS, (int)share, true).total * 8 <= max_smem_optin;
         plan->tile = 0;
         plan->threads = SMALL_CLU_WARPS * 32;
         plan->cluster = cluster;
@@ -328,8 +327,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         if (nw != 1 && nw != 2 && nw != 4 && nw != 8 && nw != 16) return fail(DN_ERR_INVALID, "warps must be 1, 2, 4, 8 or 16%s");
         long long res = 0;
         if (want_resident != 0) {
-            const long long fixed_b = small_carve(P, nw, 0).total * 8;
-            if (fixed_b + want * per_col <= max_smem_optin) res = want;
+            if (small_carve(P, nw, (int)want).total * 8 <= max_smem_optin) res = want;
         }
         if (res == 0) nw = 8;
         plan->tile = 0;

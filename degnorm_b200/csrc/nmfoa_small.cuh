@@ -227,7 +227,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
         constexpr int BLK = 32 * P;                              // doubles per block per array
         double *stage = g.stage + warp * (32 * CS);
         double *ring = g.ring + warp * (SMALL_RING * 2 * BLK);
-        const int b_lo = c_lo >> 5, b_hi = (c_hi + 31) >> 5;
+        const int b_lo = c_lo >> 5, b_hi = c_hi > c_lo ? (c_hi + 31) >> 5 : b_lo;     // (c_lo is block-aligned unless the range is empty)
         auto issue = [&](int blk) {
             if (blk < b_hi) {
                 double *dst = ring + (blk % SMALL_RING) * (2 * BLK);
