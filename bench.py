@@ -304,10 +304,14 @@ def main():
                     note="algorithmic = as-if-streamed bytes; resident genes never touch HBM again, so frac > 1 is possible",
                     resident_fraction=float((cnt[-1, :, 7] & 1).mean()),
                     nmf_calls_per_gene=float(cnt[:, :, 2].mean()), phases_ms_per_step={k: v / args.steps for k, v in all_ms.items()})
+    solves = float((cnt[:, :, 2].astype(np.float64) * (kw["nmf_iter"] + 1)).sum())
+    roofline["eig_steps_per_solve"] = float(cnt[:, :, 4].astype(np.float64).sum()) / max(solves, 1.0)
+    roofline["eig_fallback_solves"] = int((cnt[:, :, 7] >> 1).sum())
+    roofline["genes_with_fallbacks"] = int(((cnt[:, :, 7] >> 1) > 0).any(axis=0).sum())
     bk = eng.bucket_ms()
     cnt_last = cnt[-1]
     roofline["buckets"] = [dict(max_cols=bb.max_cols, genes=bb.n, threads=int(bb.plan.threads), ctas=int(bb.plan.ctas),
-                                smem=int(bb.plan.smem_bytes), resident=int(bb.plan.resident_cols),
+                                smem=int(bb.plan.smem_bytes), resident=int(bb.plan.resident_cols), cluster=int(bb.plan.cluster),
                                 end_ms=[round(bk[it][k], 2) for it in sorted(bk)],
                                 sum_cols=int(cnt_last[bb.order.cpu().numpy(), 3].sum()))
                            for k, bb in enumerate(eng.buckets)]

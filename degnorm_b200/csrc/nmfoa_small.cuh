@@ -65,6 +65,7 @@ struct SGene {
     double *xbuf;       // exchange slots: 2 alternating sets of SMALL_CLMAX x SMALL_GPART doubles (peers write here)
     int *lw;            // this CTA's width of every original bin
     int crank, csize, xpar, n0g, n_curg, goff;
+    bool primed;        // streamed tier: the ring already holds / awaits the first blocks of the next pass
     int tpack;      // this lane's Gram tile: r0 | offA << 4 | offB << 8 | u0 << 12 | u1 << 16 | u2 << 20; -1: none
 };
 
@@ -201,7 +202,7 @@ __device__ __forceinline__ void block_sum_vec(double (&x)[NV], double *part, dou
 // UPDATE=false: G = M M^T with M = x (first rank-one fit, nmf.py:88).
 // UPDATE=true : lambda <- max(0, lambda - c (K E - x)), M = x + lambda, G = M M^T (nmf.py:93-98); K E = v (v.M_old).
 template <int P, int NW, bool UPDATE, bool CLU, bool RES>
-__device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const double (&v)[P]) {
+__device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const double (&v)[P], bool prime_next) {
     using Cfg = SmallCfg<P>;
     constexpr int TC = Cfg::TC, KS = Cfg::KS, NTP = Cfg::NTP, NTILE = Cfg::NTILE, CS = P + 2, NT = NW * 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -228,13 +229,14 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
         double *stage = g.stage + warp * (32 * CS);
         double *ring = g.ring + warp * (SMALL_RING * 2 * BLK);
         const int b_lo = c_lo >> 5, b_hi = c_hi > c_lo ? (c_hi + 31) >> 5 : b_lo;     // (c_lo is block-aligned unless the range is empty)
-        auto issue = [&](int blk) {
+        // with_x: the consumer of the block is an UPDATE pass (needs x as well as M)
+        auto issue = [&](int blk, bool with_x) {
             if (blk < b_hi) {
                 double *dst = ring + (blk % SMALL_RING) * (2 * BLK);
                 const double *srcM = g.M + (long long)blk * BLK;
 #pragma unroll
                 for (int c = 0; c < BLK / 64; ++c) cp_async16(dst + (c * 32 + lane) * 2, srcM + (c * 32 + lane) * 2);
-                if constexpr (UPDATE) {
+                if (with_x) {
                     const double *srcX = g.X + (long long)blk * BLK;
 #pragma unroll
                     for (int c = 0; c < BLK / 64; ++c)
@@ -243,10 +245,13 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
             }
             cp_async_commit();
         };
+        // the first RING-1 blocks may already be on their way: the previous pass of this nmf() call primed them
+        if (!g.primed) {
 #pragma unroll
-        for (int q = 0; q < SMALL_RING - 1; ++q) issue(b_lo + q);
+            for (int q = 0; q < SMALL_RING - 1; ++q) issue(b_lo + q, UPDATE);
+        }
         for (int blk = b_lo; blk < b_hi; ++blk) {
-            issue(blk + SMALL_RING - 1);
+            issue(blk + SMALL_RING - 1, UPDATE);
             cp_async_wait<SMALL_RING - 1>();
             __syncwarp();
             const double *rm = ring + (blk % SMALL_RING) * (2 * BLK) + lane;
@@ -293,7 +298,14 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
             }
             __syncwarp();
         }
-        cp_async_wait<0>();
+        // Prime the next pass: its first blocks were written early in this one (or are the untouched x = M of the
+        // first fit), so they can travel while the Gram exchange and the eigen-solve run.
+        g.primed = prime_next;
+        if (prime_next) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < SMALL_RING - 1; ++q) issue(b_lo + q, true);
+        }
     } else {
     if constexpr (UPDATE) {
         // phase A: one lane per column; columns are independent, two in flight per lane
@@ -591,11 +603,12 @@ __device__ void run_nmf_small(const KArgs &a, SGene &g, bool first, bool want_re
     for (int k = 0; k < P; ++k) v[k] = 0.0;
     double inv_lam = 1.0;
     int hint = 0;
-    gram_small<P, NW, false, CLU, RES>(a, g, v);
-    eig_small<P, NW>(a, g, v, true, inv_lam, hint);
     const int T = a.nmf_iter;
+    g.primed = false;
+    gram_small<P, NW, false, CLU, RES>(a, g, v, T > 0);
+    eig_small<P, NW>(a, g, v, true, inv_lam, hint);
     for (int it = 0; it < T; ++it) {
-        gram_small<P, NW, true, CLU, RES>(a, g, v);
+        gram_small<P, NW, true, CLU, RES>(a, g, v, it + 1 < T);
         eig_small<P, NW>(a, g, v, false, inv_lam, hint);
     }
     final_pass_small<P, NW, CLU, RES>(a, g, v, first, want_res, e_first_g);

@@ -86,6 +86,7 @@ class ShardEngine(object):
         self.use_clusters = True
         self.force_cluster = 0
         self.clusters = (2, 4, 8, 16)
+        self.stream_clusters = ((4, 65536), (8, 262144))       # (cluster size, up to this many candidate columns)
         self.bucket_starts = {}
         self.use_row_max = use_row_max
         self.cprm = prm.to_c(p)
@@ -188,9 +189,17 @@ class ShardEngine(object):
                 if len(sel):
                     self.buckets.append(self._bucket(sel, cand, -1, cluster=cl))
                     left[sel] = False
+            # beyond the largest cluster's shared memory: streamed from per-CTA slabs, still split over a cluster whose
+            # size follows the gene (a CTA should stream at least ~16k columns per pass, or the per-iteration Gram
+            # exchange, eigen-solve and pipeline refill dominate)
+            if self.use_clusters:
+                for cl, cap in self.stream_clusters:
+                    sel = np.flatnonzero(left & (cand <= cap))
+                    if len(sel):
+                        self.buckets.append(self._bucket(sel, cand, 0, cluster=cl))
+                        left[sel] = False
             rest = np.flatnonzero(left)
             if len(rest):
-                # beyond the largest cluster's shared memory: streamed from per-CTA slabs, still split over a cluster
                 self.buckets.append(self._bucket(rest, cand, 0, cluster=(self.clusters[-1] if self.use_clusters else 0)))
             return
         for tier in RESIDENT_TIERS:
