@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SRC = [os.path.join(CSRC, f) for f in ("abi.cu", "nmfoa_tiled.cu", "nmfoa_small_p4.cu", "nmfoa_small_p8.cu",
-                                       "nmfoa_small_p12.cu")]
+                                       "nmfoa_small_p12.cu", "nmfoa_mid.cu")]
 HDR = [os.path.join(CSRC, f) for f in ("common.cuh", "launch.h", "nmfoa_small.cuh")]
 OBJ = os.path.join(HERE, "csrc", "_build")
 OUT = os.path.join(HERE, "libdegnorm_b200.so")

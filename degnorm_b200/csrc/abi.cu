@@ -247,6 +247,13 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     a.ws = (double *)((char *)workspace + 256);
     a.ws_ld = plan->ws_cols;
     DN_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
+    if (plan->tile == 6) {
+        // mid-p path (baseline selection only)
+        if (mode != MODE_BS || prm->p <= 12 || prm->p > MID_P) return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
+        a.pp = MID_P;
+        a.ws_stride = mid_slab_doubles(plan->ws_cols);
+        return dn_launch_mid(a, plan, st);
+    }
     if (plan->tile == 0) {
         // small-p path (baseline selection only)
         const int P = small_P(prm->p);
@@ -297,6 +304,25 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
     if (!plan || max_cols < 1 || sm_count < 1 || max_smem_optin < 16 * 1024) return fail(DN_ERR_INVALID, "bad planning argument%s");
     memset(plan, 0, sizeof(*plan));
     plan->cluster = 1;
+    if (!for_init && cluster >= 0 && prm->p > 12 && prm->p <= MID_P) {
+        // ---- mid-p path (13..48 samples): streamed kernel, optional cluster per gene
+        int cl = cluster > 1 ? cluster : 1;
+        if (cl != 1 && cl != 2 && cl != 4 && cl != 8 && cl != 16) return fail(DN_ERR_INVALID, "cluster must be 1, 2, 4, 8 or 16%s");
+        long long share = (max_cols + cl - 1) / cl;
+        share = (share + MID_CHUNK - 1) / MID_CHUNK * MID_CHUNK;
+        plan->tile = 6;
+        plan->threads = MID_WARPS * 32;
+        plan->cluster = cl;
+        plan->resident_cols = 0;
+        plan->smem_bytes = (int32_t)(mid_carve().total * 8);
+        plan->ws_cols = share;
+        long long clusters = sm_count / cl;
+        if (clusters > n_work) clusters = n_work;
+        if (clusters < 1) clusters = 1;
+        plan->ctas = (int32_t)(clusters * cl);
+        plan->ws_bytes = 256 + (long long)plan->ctas * mid_slab_doubles(share) * 8;
+        return DN_OK;
+    }
     const int P = for_init ? 0 : small_P(prm->p);
     if (P > 0 && cluster > 1) {
         // ---- small-p path, one thread-block cluster per gene: every CTA holds ceil(max_cols / cluster) columns

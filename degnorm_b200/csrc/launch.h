@@ -103,7 +103,40 @@ __host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols
     return (d + 31) / 32 * 32;
 }
 
+// ---- mid-p kernel (13 <= p <= 48; nmfoa_mid.cu): streamed, CTA-level cp.async ring of 64-column chunks ----------
+constexpr int MID_P = 48;             // samples padded to this
+constexpr int MID_WARPS = 8;
+constexpr int MID_CHUNK = 64;         // columns per ring stage
+constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
+constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
+
+struct MidCarve { long long small, red, binm, alive, ibuf, lw, tab, G, buf, ring, total; };
+
+__host__ __device__ inline MidCarve mid_carve() {
+    MidCarve c;
+    long long o = 0;
+    c.small = o; o += (long long)N_SMALL * MID_P;
+    c.red = o;   o += 64;
+    c.binm = o;  o += DN_MAX_BINS;
+    c.alive = o; o += DN_MAX_BINS / 2;
+    c.ibuf = o;  o += 16;
+    c.lw = o;    o += DN_MAX_BINS / 2;
+    c.tab = o;   o += 32;
+    c.G = o;     o += (long long)MID_P * MID_P;
+    c.buf = o;   o += 4ll * MID_NE;
+    c.ring = o;  o += (long long)MID_RING * 2 * MID_CHUNK * (MID_P + 2);
+    c.total = o;
+    return c;
+}
+
+// per-CTA slab (doubles): eigen fallback scratch, two exchange slots, x, M, residuals, t
+__host__ __device__ inline long long mid_slab_doubles(long long ws_cols) {
+    const long long d = 2ll * MID_P * MID_P + 2ll * MID_NE + (2ll * (MID_P + 2) + 2) * ws_cols;
+    return (d + 31) / 32 * 32;
+}
+
 // launchers (each defined in its own translation unit)
+int dn_launch_mid(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_tiled(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_small4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_small8(const KArgs &a, const dn_plan *plan, cudaStream_t st);

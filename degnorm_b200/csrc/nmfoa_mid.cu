@@ -1,0 +1,814 @@
+// degnorm_b200 -- fused baseline-selection kernel for 13..48 samples, sm_100a ("mid-p" kernel).
+//
+// Same per-gene flow as the other two kernels (reference: /root/reference/degnorm/nmf.py:189-372 around
+// nmf.py:78-107).  At p = 48 a column is 384 bytes and the Gram matrix has 1,176 entries per column: the pass is a
+// memory stream (1,152 algorithmic bytes per column-iteration) with a SYRK riding on it (~1,400 FMAs per column),
+// bound by HBM/L2 bandwidth with the FP64 pipe at roughly 40 %.  Design:
+//
+//   * one kernel, streamed: x and M = x + lambda live in per-CTA global slabs, column-major with a column stride
+//     of P + 2 doubles (the shared-memory-friendly layout, so a chunk is one flat copy); small genes simply stay
+//     in the 126 MB L2.  lambda = M - x is recovered on load, as in the small-p kernel.
+//   * the CTA (8 warps) walks its columns in 64-column chunks through a 3-stage cp.async ring (two chunks = 102 KB
+//     in flight per SM).  Phase A: 4 lanes per column (12 rows each, two xor-shuffles for t = v.M_j), new M written
+//     in place into the ring stage and to the slab.  Phase B: warp w takes the chunk's columns j = w (mod 8); its
+//     lanes own 30 tiles of 6 x 8 Gram entries that cover the upper triangle, operands straight from the stage
+//     (7 LDS.128 per 48 FMAs), accumulators stay in registers for the whole pass.  Two barriers per chunk.
+//   * per pass the 8 warps' partial Grams are summed by a fixed halving tree through shared memory; a cluster's CTAs
+//     exchange their sums through per-CTA global slots (double-buffered, one cluster barrier per pass) and add them
+//     in rank order, so every CTA holds the bit-identical G and solves redundantly (warp 0, power iteration on G in
+//     shared memory with the same guards as the other kernels).
+//   * long genes: a thread-block cluster (2..16 CTAs) per gene, contiguous column slices, exactly the scheme of the
+//     small-p cluster kernels (bins stay contiguous per CTA, drops rotate locally).
+//
+// No tensor cores: fp64 FMA pipe only.
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "launch.h"
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int MP = MID_P;                 // padded samples
+constexpr int MCS = MID_P + 2;            // column stride (doubles)
+constexpr int MNT = MID_WARPS * 32;       // threads
+constexpr int MCH = MID_CHUNK;            // columns per chunk
+constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
+constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
+
+__device__ __forceinline__ void cp_async16m(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+struct MGene {
+    double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *buf, *ring;
+    int *alive, *ibuf, *lw, *tab;
+    double *X, *M, *resb, *tb, *B0, *slots;      // global (slab)
+    long long slot_stride;                        // doubles between consecutive CTAs' slabs
+    int n0, n_cur, n0g, n_curg, goff, cs, nb0, nalive;
+    int crank, csize, xpar, eig_steps, eig_fallbacks;
+    int r0, c0;                                   // this lane's Gram tile (rows r0.., columns c0..); -1: none
+    bool primed;
+};
+
+__device__ __forceinline__ int mlstart(const MGene &g, int k) {
+    int s = 0;
+    for (int q = 0; q < k; ++q) s += g.lw[g.alive[q]];
+    return s;
+}
+
+__device__ __forceinline__ void ld12(const double *p, double (&x)[12]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const double2 t = q[i]; x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void st12(double *p, const double (&x)[12]) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) q[i] = make_double2(x[2 * i], x[2 * i + 1]);
+}
+
+// All-to-all sum over the cluster of n doubles (vals: shared, published to the CTA) through the CTAs' global slots.
+__device__ void mclu_allsum(MGene &g, const double *vals, int n, double *out) {
+    const int tid = threadIdx.x;
+    if (g.csize == 1) {
+        __syncthreads();
+        for (int k = tid; k < n; k += MNT) out[k] = vals[k];
+        __syncthreads();
+        return;
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    double *mine = g.slots + (long long)g.xpar * MNE;
+    for (int k = tid; k < n; k += MNT) mine[k] = vals[k];
+    __threadfence();
+    cl.sync();
+    const double *first = g.slots - (long long)g.crank * g.slot_stride + (long long)g.xpar * MNE;
+    for (int k = tid; k < n; k += MNT) {
+        double s = 0.0;
+        for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + k);
+        out[k] = s;
+    }
+    g.xpar ^= 1;
+    __syncthreads();
+}
+
+// ---- one pass over this CTA's columns: (optional multiplier update) + Gram of M -> G (shared, identical cluster-wide)
+template <bool UPDATE>
+__device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = g.n_cur;
+    const int nchunk = (n + MCH - 1) / MCH;
+    constexpr int STG = 2 * MCH * MCS;                     // doubles per ring stage (M then x)
+    constexpr int CPA = MCH * MCS / 2;                     // 16-byte pieces per array per chunk
+    const double c = a.c;
+    double acc[6][8];
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
+    double vq[12];
+    const int q4 = tid & 3;
+    if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
+
+    auto issue = [&](int ch, bool with_x) {
+        if (ch < nchunk) {
+            double *dst = g.ring + (ch % MID_RING) * STG;
+            const double *srcM = g.M + (long long)ch * (MCH * MCS);
+            const double *srcX = g.X + (long long)ch * (MCH * MCS);
+            for (int e = tid; e < CPA; e += MNT) cp_async16m(dst + 2 * e, srcM + 2 * e);
+            if (with_x)
+                for (int e = tid; e < CPA; e += MNT) cp_async16m(dst + MCH * MCS + 2 * e, srcX + 2 * e);
+        }
+        cp_commit();
+    };
+    if (!g.primed) {
+#pragma unroll
+        for (int q = 0; q < MID_RING - 1; ++q) issue(q, UPDATE);
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        cp_wait<MID_RING - 2>();
+        __syncthreads();                                   // chunk ch landed for everyone; stage (ch-1) is free
+        issue(ch + MID_RING - 1, UPDATE);
+        double *sM = g.ring + (ch % MID_RING) * STG;
+        const int ncol = min(MCH, n - ch * MCH);
+        if constexpr (UPDATE) {
+            // phase A: 4 lanes per column, 12 rows each
+            const int cc = tid >> 2;
+            const bool act = cc < ncol;
+            double m[12], x[12];
+            double tp = 0.0;
+            if (act) {
+                ld12(sM + cc * MCS + 12 * q4, m);
+                ld12(sM + MCH * MCS + cc * MCS + 12 * q4, x);
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int i = 0; i < 12; i += 2) { t0 = fma(vq[i], m[i], t0); t1 = fma(vq[i + 1], m[i + 1], t1); }
+                tp = t0 + t1;
+            }
+            double t = tp;                                  // (shuffles outside the branch: whole warps take part)
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            if (act) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) {
+                    const double res = fma(vq[i], t, -x[i]);
+                    const double w = fma(-c, res, m[i] - x[i]);
+                    m[i] = fma(0.5, w + fabs(w), x[i]);
+                }
+                st12(sM + cc * MCS + 12 * q4, m);
+                st12(g.M + ((long long)ch * MCH + cc) * MCS + 12 * q4, m);
+            }
+            __syncthreads();
+        }
+        // phase B: warp w sweeps columns w, w + 8, ... of the chunk; lanes own 6 x 8 tiles
+        if (g.r0 >= 0) {
+            for (int cc = warp; cc < ncol; cc += MID_WARPS) {
+                const double *mc = sM + cc * MCS;
+                const double2 a0 = *reinterpret_cast<const double2 *>(mc + g.r0);
+                const double2 a1 = *reinterpret_cast<const double2 *>(mc + g.r0 + 2);
+                const double2 a2 = *reinterpret_cast<const double2 *>(mc + g.r0 + 4);
+                const double2 u0 = *reinterpret_cast<const double2 *>(mc + g.c0);
+                const double2 u1 = *reinterpret_cast<const double2 *>(mc + g.c0 + 2);
+                const double2 u2 = *reinterpret_cast<const double2 *>(mc + g.c0 + 4);
+                const double2 u3 = *reinterpret_cast<const double2 *>(mc + g.c0 + 6);
+                const double ar[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+                const double uc[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
+            }
+        }
+    }
+    cp_wait<0>();
+    __syncthreads();
+    g.primed = prime_next;
+    if (prime_next) {
+#pragma unroll
+        for (int q = 0; q < MID_RING - 1; ++q) issue(q, true);
+    }
+    // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
+    double *mine = g.buf + (long long)(warp & 3) * MNE + lane * 48;
+    for (int half = MID_WARPS / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half && lane < MNTILE) {
+            double *dst = g.buf + (long long)(warp - half) * MNE + lane * 48;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; q += 2)
+                    *reinterpret_cast<double2 *>(dst + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+        }
+        __syncthreads();
+        if (warp < half && lane < MNTILE) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(mine + r * 8 + q);
+                    acc[r][q] += t.x;
+                    acc[r][q + 1] += t.y;
+                }
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && lane < MNTILE) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; q += 2)
+                *reinterpret_cast<double2 *>(g.buf + lane * 48 + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+    }
+    __syncthreads();
+    // ---- cluster sum (rank order) and scatter into the square G
+    const double *src = g.buf;
+    if (g.csize > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        double *slot = g.slots + (long long)g.xpar * MNE;
+        for (int e = tid; e < MNE; e += MNT) slot[e] = g.buf[e];
+        __threadfence();
+        cl.sync();
+        src = nullptr;
+    }
+    const double *first = g.slots - (long long)g.crank * g.slot_stride + (long long)g.xpar * MNE;
+    for (int e = tid; e < MNE; e += MNT) {
+        double s;
+        if (src) {
+            s = src[e];
+        } else {
+            s = 0.0;
+            for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + e);
+        }
+        const int t = e / 48, rq = e - t * 48;
+        const int i = g.tab[2 * t] + rq / 8, j = g.tab[2 * t + 1] + (rq & 7);
+        if (i <= j) {
+            g.G[i * MP + j] = s;
+            g.G[j * MP + i] = s;
+        }
+    }
+    if (g.csize > 1) g.xpar ^= 1;
+    __syncthreads();
+}
+
+// ---- top eigenvector of G (MP x MP, shared): warp 0, two rows per lane; same rules as eig_warp in nmfoa_tiled.cu
+__device__ int eig_mid_warp(const double *G, int p, double *v, bool cold, int *conv) {
+    const int lane = threadIdx.x & 31;
+    const int r0 = lane, r1 = lane + 32;
+    double v0 = 0.0, v1 = 0.0;
+    if (cold) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < p; ++k) {
+            if (r0 < p) s0 += G[k * MP + r0];
+            if (r1 < p) s1 += G[k * MP + r1];
+        }
+        const double n2 = warp_sum(s0 * s0 + s1 * s1);
+        const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
+        v0 = s0 * inv;
+        v1 = s1 * inv;
+        __syncwarp();
+        if (r0 < MP) v[r0] = v0;
+        if (r1 < MP) v[r1] = v1;
+        __syncwarp();
+    } else {
+        if (r0 < MP) v0 = v[r0];
+        if (r1 < MP) v1 = v[r1];
+    }
+    int steps = 0, ok = 0;
+    double prev = 1.0e300;
+    for (; steps < EIG_FAST_STEPS;) {
+        double y0a = 0.0, y0b = 0.0, y1a = 0.0, y1b = 0.0;
+        for (int k = 0; k < p; k += 2) {
+            const double2 vk = *reinterpret_cast<const double2 *>(v + k);
+            if (r0 < p) { y0a = fma(G[k * MP + r0], vk.x, y0a); y0b = fma(G[(k + 1) * MP + r0], vk.y, y0b); }
+            if (r1 < p) { y1a = fma(G[k * MP + r1], vk.x, y1a); y1b = fma(G[(k + 1) * MP + r1], vk.y, y1b); }
+        }
+        const double y0 = y0a + y0b, y1 = y1a + y1b;
+        ++steps;
+        const double n2 = warp_sum(y0 * y0 + y1 * y1);
+        if (!(n2 > 0.0)) {
+            v0 = v1 = 0.0;
+            __syncwarp();
+            if (r0 < MP) v[r0] = 0.0;
+            if (r1 < MP) v[r1] = 0.0;
+            __syncwarp();
+            ok = 1;
+            break;
+        }
+        const double inv = 1.0 / sqrt(n2);
+        const double w0 = y0 * inv, w1 = y1 * inv;
+        const double d = warp_max(fmax(fabs(w0 - v0), fabs(w1 - v1)));
+        v0 = w0;
+        v1 = w1;
+        __syncwarp();
+        if (r0 < MP) v[r0] = v0;
+        if (r1 < MP) v[r1] = v1;
+        __syncwarp();
+        if (d <= EIG_TOL) { ok = 1; break; }
+        if (steps >= 8 && d > 0.75 * prev) break;
+        prev = d;
+    }
+    if (ok == 1) {
+        const double m0 = (r0 < p && G[r0 * MP + r0] > 0.0) ? v0 : 1.0;
+        const double m1 = (r1 < p && G[r1 * MP + r1] > 0.0) ? v1 : 1.0;
+        const double vmin = -warp_max(-fmin(m0, m1));
+        const double vmax = warp_max(fmax(v0, v1));
+        if (vmin < EIG_SUSPECT * vmax) ok = 2;
+    }
+    if (lane == 0) *conv = ok;
+    return steps;
+}
+
+__device__ void eig_mid(const KArgs &a, MGene &g, bool cold) {
+    // (the padded rows p..MP-1 of G are zero; odd p reads one zero row past p in the unrolled loop: fine, MP is even)
+    if (threadIdx.x < 32) {
+        const int s = eig_mid_warp(g.G, (a.p + 1) & ~1, g.v, cold, g.ibuf + 12);
+        g.eig_steps += s;
+    }
+    __syncthreads();
+    const int conv = g.ibuf[12];
+    if (conv != 1) {                               // uniform across the CTA (and the cluster: same G everywhere)
+        const int s = eig_squaring<MNT>(g.G, MP, a.p, g.v, g.red, g.B0, g.B0 + MP * MP, conv == 2);
+        g.eig_steps += s;
+        g.eig_fallbacks += 1;
+    }
+}
+
+// ---- final pass of an nmf() call: t_j, residuals, row sums (see final_pass in nmfoa_tiled.cu) --------------------
+__device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_res, double *e_first_g) {
+    const int tid = threadIdx.x;
+    const int n = g.n_cur;
+    const int q4 = tid & 3;
+    double vq[12];
+    ld12(g.v + 12 * q4, vq);
+    double st = 0.0, st2 = 0.0;
+    double sF[12], sC[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { sF[i] = 0.0; sC[i] = 0.0; }
+    // 4 lanes per column again; whole warps iterate together (64 columns per CTA step)
+    const int nround = (n + MCH - 1) / MCH;
+    for (int rd = 0; rd < nround; ++rd) {
+        const int col = rd * MCH + (tid >> 2);
+        double m[12], x[12];
+        double tp = 0.0;
+        if (col < n) {
+            ld12(g.M + (long long)col * MCS + 12 * q4, m);
+            ld12(g.X + (long long)col * MCS + 12 * q4, x);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) tp = fma(vq[i], m[i], tp);
+        }
+        double t = tp;
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        double r = 0.0;
+        if (col < n) {
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const double ke = vq[i] * t;
+                const double kc = ke < x[i] ? x[i] : ke;
+                sF[i] += x[i];
+                sC[i] += kc;
+                if (want_res) {
+                    const double qv = ((first ? ke : kc) - x[i]) / (x[i] + 1.0);
+                    r = fmax(r, qv * qv);
+                }
+            }
+        }
+        r = fmax(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = fmax(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        if (col < n && q4 == 0) {
+            g.tb[col] = t;
+            if (want_res) g.resb[col] = r;
+            st += t;
+            st2 = fma(t, t, st2);
+        }
+    }
+    // reductions: st, st2 over the CTA; sF / sC over the lanes with the same q4 (rows 12 q4 .. 12 q4 + 11)
+    const double sum_t_l = block_sum<MNT>(st, g.red);
+    const double sum_t2_l = block_sum<MNT>(st2, g.red);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        // sum over lanes with equal (lane & 3): xor 4, 8, 16
+        for (int o = 4; o < 32; o <<= 1) {
+            sF[i] += __shfl_xor_sync(0xffffffffu, sF[i], o);
+            sC[i] += __shfl_xor_sync(0xffffffffu, sC[i], o);
+        }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    // buf as scratch: [warp][2][MP]
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            g.buf[(warp * 2 + 0) * MP + 12 * lane + i] = sF[i];
+            g.buf[(warp * 2 + 1) * MP + 12 * lane + i] = sC[i];
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * MP) {
+        const int which = tid / MP, i = tid - which * MP;
+        double s = 0.0;
+        for (int w = 0; w < MID_WARPS; ++w) s += g.buf[(w * 2 + which) * MP + i];
+        g.buf[MID_WARPS * 2 * MP + tid] = s;              // [0, MP): rsF, [MP, 2MP): rsC
+    }
+    if (tid == 0) { g.buf[MID_WARPS * 2 * MP + 2 * MP] = sum_t_l; g.buf[MID_WARPS * 2 * MP + 2 * MP + 1] = sum_t2_l; }
+    __syncthreads();
+    double *vals = g.buf + MID_WARPS * 2 * MP;            // 2 MP + 2 values
+    mclu_allsum(g, vals, 2 * MP + 2, vals);
+    const double sum_t = vals[2 * MP], sum_t2 = vals[2 * MP + 1];
+    const double sigma = sqrt(sum_t2);
+    if (e_first_g != nullptr) {
+        const double inv = sigma > 0.0 ? 1.0 / sigma : 0.0;
+        for (int col = tid; col < n; col += MNT) e_first_g[g.goff + col] = g.tb[col] * inv;
+    }
+    if (tid < MP) {
+        const double vi = g.v[tid];
+        g.rsF[tid] = vals[tid];
+        g.rsC[tid] = vals[MP + tid];
+        g.tmp[tid] = vi * sum_t;
+        g.K[tid] = vi * sigma;
+    }
+    __syncthreads();
+}
+
+__device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res, double *e_first_g) {
+    const int tid = threadIdx.x;
+    {   // lambda = 0: M = x
+        const double2 *src = reinterpret_cast<const double2 *>(g.X);
+        double2 *dst = reinterpret_cast<double2 *>(g.M);
+        const long long n2 = (long long)g.n_cur * (MCS / 2);
+        for (long long e = tid; e < n2; e += MNT) dst[e] = src[e];
+    }
+    __syncthreads();
+    const int T = a.nmf_iter;
+    g.primed = false;
+    gram_mid<false>(a, g, T > 0);
+    eig_mid(a, g, true);
+    for (int it = 0; it < T; ++it) {
+        gram_mid<true>(a, g, it + 1 < T);
+        eig_mid(a, g, false);
+    }
+    final_pass_mid(a, g, first, want_res, e_first_g);
+}
+
+__global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int p = a.p;
+    const MidCarve cv = mid_carve();
+    MGene g;
+    double *sm = smem + cv.small;
+    g.v = sm;            g.K = sm + MP;        g.K0 = sm + 2 * MP;   g.rs0 = sm + 3 * MP;   g.rsF = sm + 4 * MP;
+    g.rsC = sm + 5 * MP; g.rsC0 = sm + 6 * MP; g.rho = sm + 7 * MP;  g.scale = sm + 8 * MP; g.tmp = sm + 9 * MP;
+    g.red = smem + cv.red;
+    g.binm = smem + cv.binm;
+    g.alive = reinterpret_cast<int *>(smem + cv.alive);
+    g.ibuf = reinterpret_cast<int *>(smem + cv.ibuf);
+    g.lw = reinterpret_cast<int *>(smem + cv.lw);
+    g.tab = reinterpret_cast<int *>(smem + cv.tab);
+    g.G = smem + cv.G;
+    g.buf = smem + cv.buf;
+    g.ring = smem + cv.ring;
+    cg::cluster_group cl = cg::this_cluster();
+    g.crank = (int)cl.block_rank();
+    g.csize = (int)cl.num_blocks();
+    g.xpar = 0;
+    const long long wcols = a.ws_ld;                           // columns one CTA can hold
+    double *slab = a.ws + (long long)blockIdx.x * a.ws_stride;
+    g.slot_stride = a.ws_stride;
+    g.B0 = slab;
+    g.slots = slab + 2 * MP * MP;
+    g.X = g.slots + 2 * MNE;
+    g.M = g.X + (long long)MCS * wcols;
+    g.resb = g.M + (long long)MCS * wcols;
+    g.tb = g.resb + wcols;
+    {   // Gram tile of this lane (same in every warp) and the table of all tiles
+        int idx = 0;
+        g.r0 = -1; g.c0 = 0;
+        for (int rb = 0; rb < 8; ++rb)
+            for (int cb = 0; cb < 6; ++cb)
+                if (8 * cb + 7 >= 6 * rb) {
+                    if (idx == lane) { g.r0 = 6 * rb; g.c0 = 8 * cb; }
+                    if (tid == 0) { g.tab[2 * idx] = 6 * rb; g.tab[2 * idx + 1] = 8 * cb; }
+                    ++idx;
+                }
+    }
+    for (int e = tid; e < N_SMALL * MP; e += MNT) sm[e] = 0.0;
+    for (int e = tid; e < MP * MP; e += MNT) g.G[e] = 0.0;
+    g.eig_steps = 0;
+    g.eig_fallbacks = 0;
+    __syncthreads();
+    cl.sync();
+
+    for (;;) {
+        if (g.crank == 0 && tid == 0) {
+            const int t = atomicAdd(a.queue, 1);
+            for (int r = 0; r < g.csize; ++r) *cl.map_shared_rank(g.ibuf, r) = t;
+        }
+        cl.sync();
+        const int w = g.ibuf[0];
+        __syncthreads();
+        if (w >= a.n_work) break;
+        const int gid = a.order[w];
+        const long long o0 = a.off[gid];
+        const int L = (int)(a.off[gid + 1] - o0);
+        const double *F = a.cov + (long long)p * o0;
+        int *cnt = a.counters ? a.counters + (long long)gid * DN_NCOUNTERS : nullptr;
+        g.eig_steps = 0;
+        g.eig_fallbacks = 0;
+
+        if (tid < MP) g.scale[tid] = tid < p ? a.scale[tid] : 1.0;
+        __syncthreads();
+        double tmax = -1.0e300;
+        if (a.row_max) {
+            if (tid < p) tmax = a.row_max[(long long)gid * p + tid] / g.scale[tid];
+        } else {
+            for (int i = 0; i < p; ++i) {
+                const double *row = F + (long long)i * L;
+                double m = -1.0e300;
+                for (int j = tid; j < L; j += MNT) m = fmax(m, row[j]);
+                tmax = fmax(tmax, m / g.scale[i]);
+            }
+        }
+        const double gmax = block_max<MNT>(tmax, g.red);
+        const double thr = 0.1 * gmax;                                   // nmf.py:76
+        const int rate = a.rate;
+        const int start = (rate > 1 && a.ds_start) ? a.ds_start[gid] : 0;
+        const int ncand = start < L ? (L - start + rate - 1) / rate : 0;
+        const int share = (ncand + g.csize - 1) / g.csize;
+        const int k_lo = min(g.crank * share, ncand), k_hi = min(k_lo + share, ncand);
+        int exit_code = DN_EXIT_NONE;
+        int ran = 0, nmf_calls = 0, sum_cols = 0;
+        unsigned long long drops = 0ull;
+        bool k_is_refined = false;
+        int n0 = 0;
+        g.goff = 0;
+        if (share > wcols) {
+            exit_code = -1;
+        } else {
+            // keep + compact (one thread per candidate column; the 48 scaled values go straight to the slab)
+            int running = 0;
+            int *wcount = g.ibuf + 1;
+            for (int kb = k_lo; kb < k_hi; kb += MNT) {
+                const int k = kb + tid;
+                bool keep = false;
+                long long col = 0;
+                if (k < k_hi) {
+                    col = start + (long long)k * rate;
+                    double cm = -1.0e300;
+                    for (int i = 0; i < p; ++i) cm = fmax(cm, F[(long long)i * L + col] / g.scale[i]);
+                    keep = cm > thr;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (lane == 0) wcount[warp] = __popc(bal);
+                __syncthreads();
+                int pre = running, tot = 0;
+#pragma unroll
+                for (int q = 0; q < MID_WARPS; ++q) {
+                    const int cq = wcount[q];
+                    if (q < warp) pre += cq;
+                    tot += cq;
+                }
+                if (keep) {
+                    const int dst = pre + __popc(bal & ((1u << lane) - 1u));
+                    double *xc = g.X + (long long)dst * MCS;
+                    for (int i = 0; i < MCS; ++i) xc[i] = i < p ? F[(long long)i * L + col] / g.scale[i] : 0.0;
+                }
+                running += tot;
+                __syncthreads();
+            }
+            g.n0 = g.n_cur = running;
+            n0 = running;
+            if (tid < g.csize) g.binm[tid] = tid == g.crank ? (double)running : 0.0;
+            __syncthreads();
+            mclu_allsum(g, g.binm, g.csize, g.binm);
+            n0 = 0;
+            for (int r = 0; r < g.csize; ++r) {
+                if (r == g.crank) g.goff = n0;
+                n0 += (int)g.binm[r];
+            }
+            __syncthreads();
+        }
+        g.n0g = g.n_curg = n0;
+        if (exit_code == -1) {
+        } else if (n0 < a.min_hi) {
+            exit_code = DN_EXIT_FEW_HICOV;
+        } else {
+            g.cs = n0; g.nb0 = 1; g.nalive = 1;
+            if (tid == 0) { g.alive[0] = 0; g.lw[0] = g.n0; }
+            {   // rs(F_start): thread per row-quarter of a column, as in the final pass
+                const int q4 = tid & 3;
+                double rs[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) rs[i] = 0.0;
+                for (int col = tid >> 2; col < g.n0; col += MNT / 4) {
+                    double x[12];
+                    ld12(g.X + (long long)col * MCS + 12 * q4, x);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) rs[i] += x[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                    for (int o = 4; o < 32; o <<= 1) rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+                __syncthreads();
+                if (lane < 4) {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) g.buf[warp * MP + 12 * lane + i] = rs[i];
+                }
+                __syncthreads();
+                if (tid < MP) {
+                    double s = 0.0;
+                    for (int w2 = 0; w2 < MID_WARPS; ++w2) s += g.buf[w2 * MP + tid];
+                    g.rs0[tid] = s;
+                }
+                __syncthreads();
+                mclu_allsum(g, g.rs0, MP, g.rs0);
+            }
+            bool any_empty = false;
+            for (int i = 0; i < p; ++i) any_empty |= !(g.rs0[i] > 0.0);
+            if (any_empty) {
+                exit_code = DN_EXIT_EMPTY_SAMPLE;
+            } else {
+                const bool store_e = (a.e_first != nullptr) && (n0 == L);
+                bool first = true, in_loop = false;
+                double rmax = 0.0;
+                for (;;) {
+                    run_nmf_mid(a, g, first, true, (first && store_e) ? a.e_first + o0 : nullptr);
+                    nmf_calls += 1; sum_cols += g.n_curg;
+                    if (first) {
+                        if (tid < MP) {
+                            g.rho[tid] = 1.0 - g.rs0[tid] / (g.tmp[tid] + 1.0);
+                            g.K0[tid] = g.K[tid];
+                            g.rsC0[tid] = g.rsC[tid];
+                        }
+                        __syncthreads();
+                        if (median_one_minus(g.rho, p) > 1.0) { exit_code = DN_EXIT_MEDIAN; break; }
+                        double rmin = g.rho[0];
+                        rmax = g.rho[0];
+                        for (int i = 1; i < p; ++i) { rmin = fmin(rmin, g.rho[i]); rmax = fmax(rmax, g.rho[i]); }
+                        if (!(n0 >= a.min_len && rmin <= 0.2 && !a.skip)) { exit_code = DN_EXIT_NO_SELECTION; break; }
+                        g.cs = (n0 + a.bins - 1) / a.bins;
+                        g.nb0 = (n0 + g.cs - 1) / g.cs;
+                        g.nalive = g.nb0;
+                        for (int b = tid; b < g.nb0; b += MNT) {
+                            g.alive[b] = b;
+                            const int lo = max(b * g.cs, g.goff), hi = min(min((b + 1) * g.cs, n0), g.goff + g.n0);
+                            g.lw[b] = max(0, hi - lo);
+                        }
+                        __syncthreads();
+                        in_loop = true;
+                        first = false;
+                    } else {
+                        double mn = g.tmp[0];
+                        for (int i = 1; i < p; ++i) mn = fmin(mn, g.tmp[i]);
+                        if (mn == 0.0) break;
+                        __syncthreads();
+                        if (tid < MP) g.rho[tid] = 1.0 - g.rsF[tid] / (g.rsC[tid] + 1.0);
+                        __syncthreads();
+                        rmax = g.rho[0];
+                        for (int i = 1; i < p; ++i) rmax = fmax(rmax, g.rho[i]);
+                        if (g.nalive <= a.min_bins || g.n_curg < a.min_len) break;
+                    }
+                    if (!(rmax > 0.1)) break;
+                    ran = 1;
+                    for (int k = warp; k < g.nalive; k += MID_WARPS) {
+                        const int wl = g.lw[g.alive[k]];
+                        const double *rr = g.resb + mlstart(g, k);
+                        double s = 0.0;
+                        for (int j = lane; j < wl; j += 32) s += rr[j];
+                        s = warp_sum(s);
+                        if (lane == 0) g.binm[k] = s;
+                    }
+                    __syncthreads();
+                    mclu_allsum(g, g.binm, g.nalive, g.binm);
+                    int kd = 0;
+                    double best = -1.0;
+                    for (int k = 0; k < g.nalive; ++k) {
+                        const int b = g.alive[k];
+                        const double mean = g.binm[k] / (double)min(g.cs, n0 - b * g.cs);
+                        if (mean > best) { best = mean; kd = k; }
+                    }
+                    if (best == 0.0) break;
+                    const int bd = g.alive[kd];
+                    const int wd = min(g.cs, n0 - bd * g.cs);
+                    {   // rotate this CTA's share of the dropped bin to the end of its current columns (M is scratch)
+                        const int a0 = mlstart(g, kd);
+                        const int wl = g.lw[bd];
+                        const int tail = g.n_cur - a0 - wl;
+                        const int h = MCS / 2;
+                        const double2 *xs = reinterpret_cast<const double2 *>(g.X + (long long)a0 * MCS);
+                        double2 *ms = reinterpret_cast<double2 *>(g.M + (long long)a0 * MCS);
+                        double2 *xd = reinterpret_cast<double2 *>(g.X + (long long)a0 * MCS);
+                        __syncthreads();
+                        for (long long e = tid; e < (long long)(tail + wl) * h; e += MNT) ms[e] = xs[e];
+                        __syncthreads();
+                        for (long long e = tid; e < (long long)tail * h; e += MNT) xd[e] = ms[(long long)wl * h + e];
+                        for (long long e = tid; e < (long long)wl * h; e += MNT) xd[(long long)tail * h + e] = ms[e];
+                        if (tid == 0)
+                            for (int k = kd; k < g.nalive - 1; ++k) g.alive[k] = g.alive[k + 1];
+                        g.n_cur -= wl;
+                    }
+                    __syncthreads();
+                    g.nalive -= 1;
+                    g.n_curg -= wd;
+                    drops |= 1ull << bd;
+                    if (g.n_curg < 2) break;
+                }
+                if (in_loop) {
+                    __syncthreads();
+                    bool fallback = true;
+                    exit_code = DN_EXIT_FALLBACK;
+                    if (rmax < 0.2) {
+                        floor_abs(g.K, g.K, p);
+                        double s = 0.0;
+                        for (int j = tid; j < g.n0; j += MNT) {
+                            const double *xc = g.X + (long long)j * MCS;
+                            double e = -1.0e300;
+                            for (int i = 0; i < p; ++i) e = fmax(e, xc[i] / g.K[i]);
+                            s += e;
+                        }
+                        double S = block_sum<MNT>(s, g.red);
+                        if (tid == 0) g.binm[0] = S;
+                        __syncthreads();
+                        mclu_allsum(g, g.binm, 1, g.binm);
+                        S = g.binm[0];
+                        __syncthreads();
+                        if (tid < MP) g.rho[tid] = 1.0 - g.rs0[tid] / (g.K[tid] * S + 1.0);
+                        __syncthreads();
+                        rmax = g.rho[0];
+                        for (int i = 1; i < p; ++i) rmax = fmax(rmax, g.rho[i]);
+                        if (rmax > 0.9) {
+                            exit_code = DN_EXIT_FALLBACK_HIGH;
+                        } else {
+                            exit_code = DN_EXIT_REFINED;
+                            fallback = false;
+                            k_is_refined = true;
+                        }
+                    }
+                    if (fallback) {
+                        __syncthreads();
+                        if (tid < MP) g.rho[tid] = 1.0 - g.rs0[tid] / (g.rsC0[tid] + 1.0);
+                        __syncthreads();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const bool is_default = exit_code == DN_EXIT_FEW_HICOV || exit_code == DN_EXIT_EMPTY_SAMPLE ||
+                                exit_code == DN_EXIT_MEDIAN || exit_code == -1;
+        if (!is_default && !k_is_refined) {
+            if (n0 == L) {
+                if (tid < MP) g.K[tid] = g.K0[tid];
+                __syncthreads();
+            } else {
+                floor_abs(g.K0, g.K, p);
+            }
+        }
+        if (g.crank == 0) {
+            if (tid < p) {
+                double r = is_default ? 0.0 : g.rho[tid];
+                r = r > 0.9 ? 0.9 : r;
+                r = r < 0.0 ? 0.0 : r;
+                a.rho[(long long)gid * p + tid] = r;
+                if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
+            }
+            if (tid == 0) {
+                a.ran[gid] = (unsigned char)(is_default ? 0 : ran);
+                if (cnt) {
+                    cnt[DN_CNT_EXIT] = exit_code; cnt[DN_CNT_N_HICOV] = n0; cnt[DN_CNT_NMF_CALLS] = nmf_calls;
+                    cnt[DN_CNT_SUM_COLS] = sum_cols; cnt[DN_CNT_EIG_STEPS] = g.eig_steps;
+                    cnt[DN_CNT_DROPS_LO] = (int)(drops & 0xffffffffull); cnt[DN_CNT_DROPS_HI] = (int)(drops >> 32);
+                    cnt[DN_CNT_RESIDENT] = (g.eig_fallbacks << 1);
+                }
+            }
+        }
+        __syncthreads();
+        cl.sync();
+    }
+}
+
+}  // namespace
+
+int dn_launch_mid(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+    auto kern = nmfoa_mid_kernel;
+    DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
+    if (plan->cluster > 8) DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    const int cl = plan->cluster > 0 ? plan->cluster : 1;
+    cfg.gridDim = dim3(plan->ctas / cl * cl, 1, 1);
+    cfg.blockDim = dim3(MNT, 1, 1);
+    cfg.dynamicSmemBytes = plan->smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DN_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    return DN_OK;
+}

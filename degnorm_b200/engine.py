@@ -17,6 +17,9 @@ from ._lib import DnParams, DnPlan, check
 
 # resident tiers (columns) of the tiled kernel (p > 12)
 RESIDENT_TIERS = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
+# mid-p kernel (13 <= p <= 48): (cluster size, up to this many candidate columns)
+MID_MAX_P = 48
+MID_CLUSTERS = ((1, 4096), (2, 8192), (4, 16384), (8, 49152), (16, 1 << 31))
 # small-p kernel (p <= 12): (columns, warps per CTA); the column caps make whole numbers of CTAs fill an SM's 227 KB
 SMALL_TIERS = ((36, 1), (64, 1), (96, 1), (154, 2), (204, 2), (284, 2), (420, 4), (856, 8))
 
@@ -84,6 +87,7 @@ class ShardEngine(object):
         self.serial_buckets = False
         self.prioritise = True
         self.use_clusters = True
+        self.use_mid = True
         self.force_cluster = 0
         self.clusters = (2, 4, 8, 16)
         self.stream_clusters = ((4, 65536), (8, 262144))       # (cluster size, up to this many candidate columns)
@@ -167,8 +171,10 @@ class ShardEngine(object):
         cand = (L + r - 1) // r
         if self.force_streamed or self.force_cluster:
             # testing aids: everything through the streamed tier and / or through clusters of a given size
-            self.buckets.append(self._bucket(np.arange(n), cand, 0 if self.force_streamed else -1,
-                                             cluster=self.force_cluster if self.p <= 12 else 0))
+            cl = self.force_cluster if self.p <= MID_MAX_P else 0
+            if 12 < self.p <= MID_MAX_P and not self.use_mid:
+                cl = -1
+            self.buckets.append(self._bucket(np.arange(n), cand, 0 if self.force_streamed else -1, cluster=cl))
             return
         left = np.ones(n, dtype=bool)
         prev = 0
@@ -202,19 +208,28 @@ class ShardEngine(object):
             if len(rest):
                 self.buckets.append(self._bucket(rest, cand, 0, cluster=(self.clusters[-1] if self.use_clusters else 0)))
             return
+        if self.p <= MID_MAX_P and self.use_mid:
+            # mid-p kernel (13..48 samples): every gene streams from its slab; cluster size follows gene length
+            for cl, cap in MID_CLUSTERS:
+                sel = np.flatnonzero(left & (cand <= cap))
+                if len(sel):
+                    self.buckets.append(self._bucket(sel, cand, 0, cluster=cl))
+                    left[sel] = False
+            return
+        tiled = -1 if self.p <= MID_MAX_P else 0          # (13..48 samples: ask the planner for the tiled kernel)
         for tier in RESIDENT_TIERS:
-            plan = self._make_plan(tier, 1, tier)
+            plan = self._make_plan(tier, 1, tier, cluster=tiled)
             if plan.resident_cols < tier:
                 break
             sel = np.flatnonzero(left & (cand <= tier) & (cand > prev))
             if len(sel):
-                self.buckets.append(self._bucket(sel, cand, tier))
+                self.buckets.append(self._bucket(sel, cand, tier, cluster=tiled))
                 left[sel] = False
             prev = tier
         rest = np.flatnonzero(left)
         if len(rest):
             # wholly streamed: a small shared-memory footprint lets several CTAs share an SM
-            self.buckets.append(self._bucket(rest, cand, 0))
+            self.buckets.append(self._bucket(rest, cand, 0, cluster=tiled))
 
     # ---------------------------------------------------------------------------------------------------------
     def _allreduce(self, t):

@@ -80,7 +80,7 @@ typedef struct dn_params {
 
 /* Launch plan for one bucket of genes (all genes of one launch share a shared-memory carve-up). */
 typedef struct dn_plan {
-    int32_t tile;           /* 0: small-p kernel (p <= 12); 4 or 8: Gram tile edge of the tiled kernel */
+    int32_t tile;           /* 0: small-p kernel (p <= 12); 6: mid-p kernel (13..48); 4 or 8: tiled kernel's Gram tile edge */
     int32_t threads;        /* CTA size                                                         */
     int32_t ctas;           /* persistent CTAs to launch                                        */
     int32_t resident_cols;  /* columns of x and lambda held in shared memory (0: none)          */
@@ -105,6 +105,8 @@ int dn_device_info(int32_t *sm_count, int32_t *max_smem_optin, int32_t *cc);
  * warps: warps per CTA on the small-p path (1, 2, 4, 8, 16; 0 = chosen from the tier), ignored elsewhere.
  * cluster: CTAs that share one gene on the small-p path (0/1: none; 2, 4, 8, 16: a thread-block cluster whose
  * CTAs each hold ceil(max_cols/cluster) columns and exchange the partial Gram through distributed shared memory).
+ * For 13..48 samples the streamed mid-p kernel is planned (cluster 1..16); cluster = -1 asks for the generic tiled
+ * kernel instead (the path of p > 48, kept selectable for cross-checks).
  * On the small-p path (p <= 12, for_init = 0) a bucket is wholly resident (max_cols fit in shared memory) or
  * wholly streamed; on the tiled path residency is decided per gene.
  * Pure host arithmetic (no device call): sm_count / max_smem come from dn_device_info. */

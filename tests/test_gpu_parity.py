@@ -161,6 +161,36 @@ def test_cluster_path_equals_single_cta_path(p, cluster, streamed):
     np.testing.assert_allclose(a["est"], b["est"], rtol=1e-9, atol=1e-9)
 
 
+@pytest.mark.parametrize("p,cluster", [(17, 1), (48, 1), (48, 4), (30, 16)])
+def test_mid_kernel_equals_tiled_kernel(p, cluster):
+    """13..48 samples: the streamed mid-p kernel (optionally one cluster per gene) against the generic tiled
+    kernel on the same genes: identical decisions and call sequences, DI equal to rounding."""
+    import torch
+    from degnorm_b200.engine import Params, ShardEngine
+    from degnorm_b200.packing import pack_coverage
+    from degnorm_b200.synth import synth_numpy
+    lengths = np.array([300, 520, 1810, 150, 260, 2900, 410, 95])
+    mats, reads = synth_numpy(len(lengths), p, 300 + p, lengths=lengths, jitter=1e-6)
+    prm = Params(degnorm_iter=2, nmf_iter=25)
+    flat, off = pack_coverage(mats, p)
+    outs = []
+    for use_mid in (False, True):
+        eng = ShardEngine(prm, p, "cuda:0")
+        eng.use_mid = use_mid
+        eng.force_cluster = cluster if (use_mid and cluster > 1) else 0
+        eng.load(flat.cuda(), off, torch.from_numpy(reads).cuda())
+        assert all((int(b.plan.tile) == 6) == use_mid for b in eng.buckets)
+        o = eng.run(None, want_estimates=True)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items() if v is not None})
+    a, b = outs
+    np.testing.assert_array_equal(a["ran"], b["ran"])
+    np.testing.assert_array_equal(a["counters"][:, :, :4], b["counters"][:, :, :4])
+    np.testing.assert_array_equal(a["counters"][:, :, 5:7], b["counters"][:, :, 5:7])
+    np.testing.assert_allclose(a["rho"], b["rho"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(a["est"], b["est"], rtol=1e-9, atol=1e-9)
+
+
 def test_init_pass_matches_kat():
     """ratio_svd known-answer vector (produced by the reference)."""
     import os

@@ -87,9 +87,15 @@ def test_plan_is_pure_host_arithmetic():
     # the init pass and p > 12 use the tiled kernel
     assert lib.dn_make_plan(C.byref(prm), 5000, 1000, 0, 1, 0, 0, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 4 and plan.threads == 256
+    # 13..48 samples: the streamed mid-p kernel (tile 6), one cluster per long gene; cluster = -1 asks for the tiled one
     prm48 = Params().to_c(48)
-    assert lib.dn_make_plan(C.byref(prm48), 100000, 1000, -1, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert lib.dn_make_plan(C.byref(prm48), 100000, 1000, 0, 0, 0, 16, 148, 232448, C.byref(plan)) == 0
+    assert plan.tile == 6 and plan.cluster == 16 and plan.resident_cols == 0 and 16 * plan.ws_cols >= 100000
+    assert plan.ws_cols % 64 == 0 and plan.ctas % 16 == 0 and plan.smem_bytes <= 232448
+    assert lib.dn_make_plan(C.byref(prm48), 100000, 1000, -1, 0, 0, -1, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 4 and 0 < plan.resident_cols < 100000 and plan.ws_cols >= 100000
+    prm64 = Params().to_c(64)
+    assert lib.dn_make_plan(C.byref(prm64), 5000, 1000, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0 and plan.tile == 4
     bad = Params().to_c(1)
     assert lib.dn_make_plan(C.byref(bad), 128, 10, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
     assert b"2 samples" in lib.dn_last_error()
