@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--serial-buckets", action="store_true", help="tuning: run the tiers one after another")
     ap.add_argument("--force-cluster", type=int, default=0, help="tuning: every gene through clusters of this size")
     ap.add_argument("--force-streamed", action="store_true", help="tuning: every gene through the streamed tier")
+    ap.add_argument("--max-len", type=int, default=0, help="tuning: clip gene lengths (removes the long-gene tail)")
     ap.add_argument("--tiers", default="", help="small-p tiers as cols:warps,... (tuning)")
     return ap.parse_args()
 
@@ -234,6 +235,8 @@ def main():
     # ---- synthetic batch, generated on the device (each rank its own seed)
     n, p = cfg["n_genes"], cfg["p"]
     lengths = config_lengths(args.config, n)
+    if args.max_len:
+        lengths = np.minimum(lengths, args.max_len)
     if world > 1:
         lengths = np.random.default_rng(cfg["seed"] + 1000 * rank).permutation(lengths)
     cov, off, reads = synth_torch(lengths, p, cfg["seed"] + 1000 * rank, dev)

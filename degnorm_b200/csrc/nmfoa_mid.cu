@@ -114,6 +114,9 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     double vq[12];
     const int q4 = tid & 3;
     if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
+    // this lane's tile, read from the shared table (a load is not rematerialised inside the chunk loop)
+    const int tr0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane) : -1;
+    const int tc0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane + 1) : 0;
 
     auto issue = [&](int ch, bool with_x) {
         if (ch < nchunk) {
@@ -166,16 +169,17 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             __syncthreads();
         }
         // phase B: warp w sweeps columns w, w + 8, ... of the chunk; lanes own 6 x 8 tiles
-        if (g.r0 >= 0) {
+        if (tr0 >= 0) {
+#pragma unroll 1
             for (int cc = warp; cc < ncol; cc += MID_WARPS) {
                 const double *mc = sM + cc * MCS;
-                const double2 a0 = *reinterpret_cast<const double2 *>(mc + g.r0);
-                const double2 a1 = *reinterpret_cast<const double2 *>(mc + g.r0 + 2);
-                const double2 a2 = *reinterpret_cast<const double2 *>(mc + g.r0 + 4);
-                const double2 u0 = *reinterpret_cast<const double2 *>(mc + g.c0);
-                const double2 u1 = *reinterpret_cast<const double2 *>(mc + g.c0 + 2);
-                const double2 u2 = *reinterpret_cast<const double2 *>(mc + g.c0 + 4);
-                const double2 u3 = *reinterpret_cast<const double2 *>(mc + g.c0 + 6);
+                const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
+                const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
+                const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
+                const double2 u0 = *reinterpret_cast<const double2 *>(mc + tc0);
+                const double2 u1 = *reinterpret_cast<const double2 *>(mc + tc0 + 2);
+                const double2 u2 = *reinterpret_cast<const double2 *>(mc + tc0 + 4);
+                const double2 u3 = *reinterpret_cast<const double2 *>(mc + tc0 + 6);
                 const double ar[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
                 const double uc[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
 #pragma unroll
@@ -254,82 +258,83 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     __syncthreads();
 }
 
-// ---- top eigenvector of G (MP x MP, shared): warp 0, two rows per lane; same rules as eig_warp in nmfoa_tiled.cu
-__device__ int eig_mid_warp(const double *G, int p, double *v, bool cold, int *conv) {
-    const int lane = threadIdx.x & 31;
-    const int r0 = lane, r1 = lane + 32;
-    double v0 = 0.0, v1 = 0.0;
+// ---- top eigenvector of G (MP x MP, shared); same rules as eig_warp in nmfoa_tiled.cu -----------------------------
+// The 48 x 48 mat-vec is spread over 240 threads (thread = row i, k-range of ten), warp 0 combines the partial
+// products, normalises and tests: two barriers per step instead of one warp doing 2 x 48 FMAs and as many shared
+// loads per lane while seven warps wait.
+__device__ int eig_mid_block(const double *G, int p, double *v, double *part, int *flag, bool cold) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = tid % MP, ks = tid / MP;
+    const int k_lo = ks * 10;
+    double gk[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) gk[j] = (ks < 5 && k_lo + j < MP) ? G[(k_lo + j) * MP + i] : 0.0;
     if (cold) {
-        double s0 = 0.0, s1 = 0.0;
-        for (int k = 0; k < p; ++k) {
-            if (r0 < p) s0 += G[k * MP + r0];
-            if (r1 < p) s1 += G[k * MP + r1];
-        }
-        const double n2 = warp_sum(s0 * s0 + s1 * s1);
-        const double inv = n2 > 0.0 ? 1.0 / sqrt(n2) : 0.0;
-        v0 = s0 * inv;
-        v1 = s1 * inv;
-        __syncwarp();
-        if (r0 < MP) v[r0] = v0;
-        if (r1 < MP) v[r1] = v1;
-        __syncwarp();
-    } else {
-        if (r0 < MP) v0 = v[r0];
-        if (r1 < MP) v1 = v[r1];
+        // G.1 (row sums) is the first iterate: start from the ones vector over the real samples
+        if (tid < MP) v[tid] = tid < p ? 1.0 : 0.0;
     }
+    __syncthreads();
     int steps = 0, ok = 0;
     double prev = 1.0e300;
-    for (; steps < EIG_FAST_STEPS;) {
-        double y0a = 0.0, y0b = 0.0, y1a = 0.0, y1b = 0.0;
-        for (int k = 0; k < p; k += 2) {
-            const double2 vk = *reinterpret_cast<const double2 *>(v + k);
-            if (r0 < p) { y0a = fma(G[k * MP + r0], vk.x, y0a); y0b = fma(G[(k + 1) * MP + r0], vk.y, y0b); }
-            if (r1 < p) { y1a = fma(G[k * MP + r1], vk.x, y1a); y1b = fma(G[(k + 1) * MP + r1], vk.y, y1b); }
+    for (; steps < EIG_FAST_STEPS + 1;) {
+        if (ks < 5) {
+            double y = 0.0;
+#pragma unroll
+            for (int j = 0; j < 10; ++j) y = fma(gk[j], (k_lo + j < MP) ? v[k_lo + j] : 0.0, y);
+            part[ks * MP + i] = y;
         }
-        const double y0 = y0a + y0b, y1 = y1a + y1b;
+        __syncthreads();
         ++steps;
-        const double n2 = warp_sum(y0 * y0 + y1 * y1);
-        if (!(n2 > 0.0)) {
-            v0 = v1 = 0.0;
-            __syncwarp();
-            if (r0 < MP) v[r0] = 0.0;
-            if (r1 < MP) v[r1] = 0.0;
-            __syncwarp();
-            ok = 1;
-            break;
+        if (warp == 0) {
+            const int r0 = lane, r1 = lane + 32;
+            double y0 = 0.0, y1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                y0 += part[q * MP + r0];
+                if (r1 < MP) y1 += part[q * MP + r1];
+            }
+            const double v0 = v[r0], v1 = r1 < MP ? v[r1] : 0.0;
+            const double n2 = warp_sum(y0 * y0 + y1 * y1);
+            int code = 0;
+            if (!(n2 > 0.0)) {
+                v[r0] = 0.0;
+                if (r1 < MP) v[r1] = 0.0;
+                code = 1;
+            } else {
+                const double inv = 1.0 / sqrt(n2);
+                const double w0 = y0 * inv, w1 = y1 * inv;
+                const double d = warp_max(fmax(fabs(w0 - v0), fabs(w1 - v1)));
+                v[r0] = w0;
+                if (r1 < MP) v[r1] = w1;
+                if (d <= EIG_TOL) {
+                    // warm-start distrust rule (see eig_warp in nmfoa_tiled.cu)
+                    const double m0 = (r0 < p && G[r0 * MP + r0] > 0.0) ? w0 : 1.0;
+                    const double m1 = (r1 < p && G[r1 * MP + r1] > 0.0) ? w1 : 1.0;
+                    const double vmin = -warp_max(-fmin(m0, m1));
+                    const double vmax = warp_max(fmax(w0, w1));
+                    code = vmin < EIG_SUSPECT * vmax ? 2 : 1;
+                } else if (steps >= 9 && d > 0.75 * prev) {
+                    code = 3;                      // small spectral gap: let the squaring solver finish
+                }
+                prev = d;
+            }
+            if (lane == 0) *flag = code;
         }
-        const double inv = 1.0 / sqrt(n2);
-        const double w0 = y0 * inv, w1 = y1 * inv;
-        const double d = warp_max(fmax(fabs(w0 - v0), fabs(w1 - v1)));
-        v0 = w0;
-        v1 = w1;
-        __syncwarp();
-        if (r0 < MP) v[r0] = v0;
-        if (r1 < MP) v[r1] = v1;
-        __syncwarp();
-        if (d <= EIG_TOL) { ok = 1; break; }
-        if (steps >= 8 && d > 0.75 * prev) break;
-        prev = d;
+        __syncthreads();
+        ok = *flag;
+        if (ok != 0) break;
     }
-    if (ok == 1) {
-        const double m0 = (r0 < p && G[r0 * MP + r0] > 0.0) ? v0 : 1.0;
-        const double m1 = (r1 < p && G[r1 * MP + r1] > 0.0) ? v1 : 1.0;
-        const double vmin = -warp_max(-fmin(m0, m1));
-        const double vmax = warp_max(fmax(v0, v1));
-        if (vmin < EIG_SUSPECT * vmax) ok = 2;
-    }
-    if (lane == 0) *conv = ok;
+    __syncthreads();
+    *flag = (ok == 1) ? 1 : (ok == 2 ? 2 : 0);
     return steps;
 }
 
 __device__ void eig_mid(const KArgs &a, MGene &g, bool cold) {
-    // (the padded rows p..MP-1 of G are zero; odd p reads one zero row past p in the unrolled loop: fine, MP is even)
-    if (threadIdx.x < 32) {
-        const int s = eig_mid_warp(g.G, (a.p + 1) & ~1, g.v, cold, g.ibuf + 12);
-        g.eig_steps += s;
-    }
+    const int s0 = eig_mid_block(g.G, a.p, g.v, g.buf, g.ibuf + 12, cold);
+    g.eig_steps += s0;
     __syncthreads();
     const int conv = g.ibuf[12];
+    __syncthreads();
     if (conv != 1) {                               // uniform across the CTA (and the cluster: same G everywhere)
         const int s = eig_squaring<MNT>(g.G, MP, a.p, g.v, g.red, g.B0, g.B0 + MP * MP, conv == 2);
         g.eig_steps += s;
