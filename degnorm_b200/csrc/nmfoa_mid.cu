@@ -117,6 +117,9 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     // this lane's tile, read from the shared table (a load is not rematerialised inside the chunk loop)
     const int tr0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane) : -1;
     const int tc0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane + 1) : 0;
+    const int rot = tc0 >> 4;
+    const int uo0 = tc0 + 2 * ((0 + rot) & 3), uo1 = tc0 + 2 * ((1 + rot) & 3), uo2 = tc0 + 2 * ((2 + rot) & 3),
+              uo3 = tc0 + 2 * ((3 + rot) & 3);
 
     auto issue = [&](int ch, bool with_x) {
         if (ch < nchunk) {
@@ -176,10 +179,13 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
                 const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
                 const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
                 const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
-                const double2 u0 = *reinterpret_cast<const double2 *>(mc + tc0);
-                const double2 u1 = *reinterpret_cast<const double2 *>(mc + tc0 + 2);
-                const double2 u2 = *reinterpret_cast<const double2 *>(mc + tc0 + 4);
-                const double2 u3 = *reinterpret_cast<const double2 *>(mc + tc0 + 6);
+                // the four column pairs are fetched in an order rotated by (c0 / 16): in every one of the four load
+                // instructions the lanes whose c0 differ by 16 or 32 doubles (same banks) then read different
+                // pairs, so the loads are bank-conflict free; the accumulator columns are un-rotated when G is built
+                const double2 u0 = *reinterpret_cast<const double2 *>(mc + uo0);
+                const double2 u1 = *reinterpret_cast<const double2 *>(mc + uo1);
+                const double2 u2 = *reinterpret_cast<const double2 *>(mc + uo2);
+                const double2 u3 = *reinterpret_cast<const double2 *>(mc + uo3);
                 const double ar[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
                 const double uc[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
 #pragma unroll
@@ -248,7 +254,8 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + e);
         }
         const int t = e / 48, rq = e - t * 48;
-        const int i = g.tab[2 * t] + rq / 8, j = g.tab[2 * t + 1] + (rq & 7);
+        const int c0t = g.tab[2 * t + 1], q = rq & 7;
+        const int i = g.tab[2 * t] + rq / 8, j = c0t + 2 * (((q >> 1) + (c0t >> 4)) & 3) + (q & 1);
         if (i <= j) {
             g.G[i * MP + j] = s;
             g.G[j * MP + i] = s;
