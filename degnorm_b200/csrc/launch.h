@@ -110,7 +110,7 @@ constexpr int MID_CHUNK = 64;         // columns per ring stage
 constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
 constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
 
-struct MidCarve { long long small, red, binm, alive, ibuf, lw, tab, G, buf, ring, total; };
+struct MidCarve { long long small, red, binm, alive, ibuf, lw, tab, mbar, G, buf, ring, total; };
 
 __host__ __device__ inline MidCarve mid_carve() {
     MidCarve c;
@@ -122,6 +122,7 @@ __host__ __device__ inline MidCarve mid_carve() {
     c.ibuf = o;  o += 16;
     c.lw = o;    o += DN_MAX_BINS / 2;
     c.tab = o;   o += 32;
+    c.mbar = o;  o += 4;                        // MID_RING mbarriers
     c.G = o;     o += (long long)MID_P * MID_P;
     c.buf = o;   o += 4ll * MID_NE;
     c.ring = o;  o += (long long)MID_RING * 2 * MID_CHUNK * (MID_P + 2);

@@ -8,8 +8,8 @@
 //   * one kernel, streamed: x and M = x + lambda live in per-CTA global slabs, column-major with a column stride
 //     of P + 2 doubles (the shared-memory-friendly layout, so a chunk is one flat copy); small genes simply stay
 //     in the 126 MB L2.  lambda = M - x is recovered on load, as in the small-p kernel.
-//   * the CTA (8 warps) walks its columns in 64-column chunks through a 3-stage cp.async ring (two chunks = 102 KB
-//     in flight per SM).  Phase A: 4 lanes per column (12 rows each, two xor-shuffles for t = v.M_j), new M written
+//   * the CTA (8 warps) walks its columns in 64-column chunks through a 3-stage ring filled by TMA 1-D bulk copies
+//     (cp.async.bulk + one mbarrier per stage; two chunks = 102 KB in flight per SM).  Phase A: 4 lanes per column (12 rows each, two xor-shuffles for t = v.M_j), new M written
 //     in place into the ring stage and to the slab.  Phase B: warp w takes the chunk's columns j = w (mod 8); its
 //     lanes own 30 tiles of 6 x 8 Gram entries that cover the upper triangle, operands straight from the stage
 //     (7 LDS.128 per 48 FMAs), accumulators stay in registers for the whole pass.  Two barriers per chunk.
@@ -35,15 +35,35 @@ constexpr int MCH = MID_CHUNK;            // columns per chunk
 constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
 constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
 
-__device__ __forceinline__ void cp_async16m(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers --------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// generic-proxy accesses (ordinary loads / stores, already ordered by a barrier) before async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 struct MGene {
     double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *buf, *ring;
@@ -54,6 +74,8 @@ struct MGene {
     int crank, csize, xpar, eig_steps, eig_fallbacks;
     int r0, c0;                                   // this lane's Gram tile (rows r0.., columns c0..); -1: none
     bool primed;
+    unsigned long long *mbar;                      // MID_RING mbarriers (one per ring stage)
+    unsigned use0, use1, use2;                      // completed fills per stage (phase parity of its mbarrier)
 };
 
 __device__ __forceinline__ int mlstart(const MGene &g, int k) {
@@ -104,7 +126,6 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     const int n = g.n_cur;
     const int nchunk = (n + MCH - 1) / MCH;
     constexpr int STG = 2 * MCH * MCS;                     // doubles per ring stage (M then x)
-    constexpr int CPA = MCH * MCS / 2;                     // 16-byte pieces per array per chunk
     const double c = a.c;
     double acc[6][8];
 #pragma unroll
@@ -121,25 +142,35 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     const int uo0 = tc0 + 2 * ((0 + rot) & 3), uo1 = tc0 + 2 * ((1 + rot) & 3), uo2 = tc0 + 2 * ((2 + rot) & 3),
               uo3 = tc0 + 2 * ((3 + rot) & 3);
 
+    // One thread hands a chunk (25.6 KB of M, and of x for an update pass) to the TMA unit; the bytes land in the
+    // ring stage and complete the stage's mbarrier.  Callers guarantee (by a __syncthreads) that nobody still uses
+    // the stage and that the slab holds the data (ordinary stores of the previous pass): the proxy fence orders
+    // those generic-proxy accesses before the async-proxy copy.
     auto issue = [&](int ch, bool with_x) {
-        if (ch < nchunk) {
-            double *dst = g.ring + (ch % MID_RING) * STG;
-            const double *srcM = g.M + (long long)ch * (MCH * MCS);
-            const double *srcX = g.X + (long long)ch * (MCH * MCS);
-            for (int e = tid; e < CPA; e += MNT) cp_async16m(dst + 2 * e, srcM + 2 * e);
-            if (with_x)
-                for (int e = tid; e < CPA; e += MNT) cp_async16m(dst + MCH * MCS + 2 * e, srcX + 2 * e);
+        if (tid == 0 && ch < nchunk) {
+            const int st = ch % MID_RING;
+            double *dst = g.ring + st * STG;
+            const unsigned bytes = MCH * MCS * 8;
+            fence_proxy_async();
+            mbar_expect_tx(g.mbar + st, with_x ? 2 * bytes : bytes);
+            bulk_g2s(dst, g.M + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
+            if (with_x) bulk_g2s(dst + MCH * MCS, g.X + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
         }
-        cp_commit();
+    };
+    auto wait_stage = [&](int ch) {
+        const int st = ch % MID_RING;
+        const unsigned par = (st == 0 ? g.use0 : (st == 1 ? g.use1 : g.use2)) & 1u;
+        mbar_wait(g.mbar + st, par);
+        if (st == 0) ++g.use0; else if (st == 1) ++g.use1; else ++g.use2;
     };
     if (!g.primed) {
 #pragma unroll
         for (int q = 0; q < MID_RING - 1; ++q) issue(q, UPDATE);
     }
     for (int ch = 0; ch < nchunk; ++ch) {
-        cp_wait<MID_RING - 2>();
-        __syncthreads();                                   // chunk ch landed for everyone; stage (ch-1) is free
+        __syncthreads();                                   // everyone is done with stage (ch - 1): refill it
         issue(ch + MID_RING - 1, UPDATE);
+        wait_stage(ch);                                    // chunk ch has landed
         double *sM = g.ring + (ch % MID_RING) * STG;
         const int ncol = min(MCH, n - ch * MCH);
         if constexpr (UPDATE) {
@@ -195,7 +226,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             }
         }
     }
-    cp_wait<0>();
+    fence_proxy_async();
     __syncthreads();
     g.primed = prime_next;
     if (prime_next) {
@@ -453,6 +484,7 @@ __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res,
         const long long n2 = (long long)g.n_cur * (MCS / 2);
         for (long long e = tid; e < n2; e += MNT) dst[e] = src[e];
     }
+    fence_proxy_async();                  // the slab was written with ordinary stores; the TMA reads it next
     __syncthreads();
     const int T = a.nmf_iter;
     g.primed = false;
@@ -483,6 +515,12 @@ __global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
     g.G = smem + cv.G;
     g.buf = smem + cv.buf;
     g.ring = smem + cv.ring;
+    g.mbar = reinterpret_cast<unsigned long long *>(smem + cv.mbar);
+    g.use0 = g.use1 = g.use2 = 0;
+    if (tid == 0) {
+        for (int q = 0; q < MID_RING; ++q) mbar_init(g.mbar + q, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
     cg::cluster_group cl = cg::this_cluster();
     g.crank = (int)cl.block_rank();
     g.csize = (int)cl.num_blocks();

@@ -534,7 +534,7 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
 template <int P, int NW, bool CLU, bool RES>
 __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P], bool first, bool want_res,
                                  double *e_first_g) {
-    constexpr int NT = NW * 32, CS = P + 2, NV = 2 + 2 * P;
+    constexpr int NT = NW * 32, NV = 2 + 2 * P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = g.n_cur;
     double acc[NV];
