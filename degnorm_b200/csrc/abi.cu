@@ -16,13 +16,14 @@ namespace {
 // ---- estimates (last outer iteration only): nmf.py:217, 247, 333-337, 343-344, 350-351, 358-365 -----------------
 __global__ void __launch_bounds__(256) estimates_kernel(const double *cov, const long long *off, const int *order,
                                                         int n_work, int p, const double *scale, const int *counters,
-                                                        const double *kfac, const double *e_first, double *est) {
+                                                        const double *kfac, const double *e_first,
+                                                        const long long *est_off, double *est) {
     for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         const int gid = order[w];
         const long long o0 = off[gid];
         const int L = (int)(off[gid + 1] - o0);
         const double *F = cov + (long long)p * o0;
-        double *out = est + (long long)p * o0;
+        double *out = est + (long long)p * (est_off ? est_off[gid] : o0);
         const int ex = counters[(long long)gid * DN_NCOUNTERS + DN_CNT_EXIT];
         const int n0 = counters[(long long)gid * DN_NCOUNTERS + DN_CNT_N_HICOV];
         const double *K = kfac + (long long)gid * p;
@@ -428,15 +429,15 @@ int dn_baseline_selection(const double *cov, const int64_t *off, const int32_t *
 }
 
 int dn_estimates(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work, const dn_params *prm,
-                 const double *scale, const int32_t *counters, const double *kfac, const double *e_first, double *est,
-                 void *stream) {
+                 const double *scale, const int32_t *counters, const double *kfac, const double *e_first,
+                 const int64_t *est_off, double *est, void *stream) {
     int rc = check_params(prm);
     if (rc) return rc;
     if (!cov || !off || !order || !scale || !counters || !kfac || !est) return fail(DN_ERR_INVALID, "null pointer argument%s");
     if (n_work <= 0) return DN_OK;
     int grid = n_work < 148 * 8 ? n_work : 148 * 8;
     estimates_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(cov, (const long long *)off, order, n_work, prm->p, scale,
-                                                             counters, kfac, e_first, est);
+                                                             counters, kfac, e_first, (const long long *)est_off, est);
     DN_CUDA(cudaGetLastError());
     return DN_OK;
 }

@@ -69,7 +69,7 @@ def _ptr(t):
 
 
 class _Bucket(object):
-    __slots__ = ("plan", "order", "n", "ws", "stream", "max_cols")
+    __slots__ = ("plan", "order", "n", "ws", "stream", "max_cols", "est_lo", "est_hi")
 
 
 class ShardEngine(object):
@@ -145,6 +145,16 @@ class ShardEngine(object):
             b.stream = torch.cuda.Stream(device=self.device, priority=max(hi, min(lo, hi + k)) if self.prioritise else 0)
         if self.init_bucket is not None:
             self.init_bucket.stream = torch.cuda.Stream(device=self.device)
+        # estimate layout in work order (used when the estimates travel to the host bucket by bucket)
+        self.est_off = np.zeros(max(self.n, 1), dtype=np.int64)
+        pos = 0
+        for b in self.buckets:
+            ids = b.order.cpu().numpy()
+            b.est_lo = pos
+            self.est_off[ids] = pos + np.concatenate(([0], np.cumsum(self.lengths[ids])[:-1]))
+            pos += int(self.lengths[ids].sum())
+            b.est_hi = pos
+        self.est_off_dev = torch.from_numpy(self.est_off).to(self.device)
 
     def _cluster_share_cap(self, cl):
         """Largest per-CTA column share a resident cluster plan accepts (pure host arithmetic)."""
@@ -238,8 +248,11 @@ class ShardEngine(object):
         elif self.group is not None:
             torch.distributed.all_reduce(t, group=self.group)
 
-    def run(self, ds_offsets=None, want_estimates=True):
-        """ds_offsets: int32 numpy [degnorm_iter, n] (this shard's genes) or None.  Results -> self.out."""
+    def run(self, ds_offsets=None, want_estimates=True, est_host=None):
+        """ds_offsets: int32 numpy [degnorm_iter, n] (this shard's genes) or None.  Results -> self.out.
+        est_host: pinned float64 host tensor of p * sum(L) elements: the estimates are then laid out in WORK order
+        (bucket by bucket, self.est_off) and each bucket's block is copied to the host as soon as the bucket has
+        finished its last outer iteration, overlapping the other buckets' compute."""
         prm, p, n, dev, lib = self.prm, self.p, self.n, self.device, self.lib
         f64 = dict(dtype=torch.float64, device=dev)
         main = torch.cuda.current_stream(dev)
@@ -263,6 +276,8 @@ class ShardEngine(object):
         want_e_first = want_estimates and prm.downsample_rate == 1 and n > 0
         e_first = torch.zeros(int(self.offsets_np[-1]), **f64) if want_e_first else None
         ds_dev = torch.from_numpy(np.ascontiguousarray(ds_offsets, dtype=np.int32)).to(dev) if ds_offsets is not None else None
+        est = torch.empty_like(self.cov) if (want_estimates and n > 0 and n_iter > 0) else None
+        overlap_est = est is not None and est_host is not None
         self.launches = 0
         self.events = []
         self.bucket_events = []
@@ -311,6 +326,15 @@ class ShardEngine(object):
                     _ptr(e_first) if (last and e_first is not None) else C.c_void_p(0),
                     _ptr(b.ws), b.ws.numel(), C.c_void_p(b.stream.cuda_stream)))
                 self.launches += 1
+                if overlap_est and last:
+                    # this bucket's estimates, then their trip to the host, behind the bucket's own kernel
+                    check(lib.dn_estimates(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm),
+                                           _ptr(scale_used), _ptr(counters[it]), _ptr(kfac), _ptr(e_first),
+                                           _ptr(self.est_off_dev), _ptr(est), C.c_void_p(b.stream.cuda_stream)))
+                    self.launches += 1
+                    lo, hi = p * int(b.est_lo), p * int(b.est_hi)
+                    with torch.cuda.stream(b.stream):
+                        est_host[lo:hi].copy_(est[lo:hi], non_blocking=True)
                 if self.record_events:
                     ev = torch.cuda.Event(enable_timing=True)
                     ev.record(b.stream)
@@ -329,18 +353,16 @@ class ShardEngine(object):
                                      _ptr(scale), C.c_void_p(main.cuda_stream)))
             self.launches += 1
 
-        est = None
-        if want_estimates and n > 0 and n_iter > 0:
-            est = torch.empty_like(self.cov)
+        if want_estimates and n > 0 and n_iter > 0 and not overlap_est:
             b = self.init_bucket
             check(lib.dn_estimates(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm),
-                                   _ptr(scale_used), _ptr(counters[n_iter - 1]), _ptr(kfac), _ptr(e_first), _ptr(est),
-                                   C.c_void_p(main.cuda_stream)))
+                                   _ptr(scale_used), _ptr(counters[n_iter - 1]), _ptr(kfac), _ptr(e_first),
+                                   C.c_void_p(0), _ptr(est), C.c_void_p(main.cuda_stream)))
             self.launches += 1
         mark("end")
         self.out = dict(rho=rho[:n], rho0=rho0[:n], x_adj=x_adj[:n], x_weighted=x_w[:n], norm_factors=norm,
                         scale_factors=scale, ran=ran[:, :n], counters=counters[:, :n], init_counters=init_counters[:n],
-                        est=est, kfac=kfac[:n], scale_used=scale_used)
+                        est=est, kfac=kfac[:n], scale_used=scale_used, est_in_work_order=overlap_est)
         return self.out
 
     # ---------------------------------------------------------------------------------------------------------

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from .engine import Params, ShardEngine, draw_offsets
-from .packing import pack_coverage, unpack_estimates
+from .packing import pack_coverage, pinned_buffer, unpack_estimates
 
 
 class GeneNMFOA(object):
@@ -138,7 +138,10 @@ class GeneNMFOA(object):
             eng = ShardEngine(self._prm, self.p, dev, group=self._group)
             eng.load(cov_dev, offsets, reads_dev)
             ds = draw_offsets(self.n_genes, self._prm)        # also seeds the global numpy stream (nmf.py:556)
-            out = eng.run(ds, want_estimates=self.return_estimates)
+            est_host = None
+            if self.return_estimates and self.n_genes > 0 and self.degnorm_iter > 0:
+                est_host = pinned_buffer(flat.numel(), "est", self._host_cache)
+            out = eng.run(ds, want_estimates=self.return_estimates, est_host=est_host)
             torch.cuda.synchronize(dev)
             t2 = time.perf_counter()
             self.rho = out["rho"].cpu().numpy()
@@ -150,7 +153,13 @@ class GeneNMFOA(object):
             self.counters = out["counters"].cpu().numpy()
             estimates = None
             if self.return_estimates and out["est"] is not None:
-                estimates = unpack_estimates(out["est"], offsets, self.p, cache=self._host_cache)
+                if out["est_in_work_order"]:
+                    # already on the host (copied bucket by bucket behind the last iteration): views in gene order
+                    arr, eo, p_ = est_host.numpy(), eng.est_off, self.p
+                    estimates = [arr[p_ * int(eo[g]): p_ * (int(eo[g]) + m.shape[1])].reshape(p_, -1)
+                                 for g, m in enumerate(cov_mats)]
+                else:
+                    estimates = unpack_estimates(out["est"], offsets, self.p, cache=self._host_cache)
             t3 = time.perf_counter()
         self._engine = eng
         self.fitted = True

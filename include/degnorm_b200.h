@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 3
+#define DN_ABI_VERSION 4
 #define DN_MAX_BINS 64      /* baseline-selection bins held in the fused kernel (reference default: 20) */
 #define DN_MAX_SAMPLES 256  /* p supported by the fused kernels (one thread per sample in the n x p steps) */
 #define DN_NCOUNTERS 8      /* int32 counters per gene, see dn_counter */
@@ -138,10 +138,13 @@ int dn_baseline_selection(const double *cov, const int64_t *off, const int32_t *
                           void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Replaces the estimate assembly at nmf.py:217, 247, 333-365 for the last outer iteration: writes the
- * p x L_g estimate of every listed gene into est (same ragged layout as cov). */
+ * p x L_g estimate of every listed gene into est.  est_off (n_genes int64, or NULL): column offset of gene g's
+ * block in est (block = est[p*est_off[g] ..]); NULL means the same ragged layout as cov.  A caller that wants the
+ * device-to-host copy of the estimates to overlap the last iteration lays est out in work order and calls this
+ * per bucket, on the bucket's stream, right after dn_baseline_selection. */
 int dn_estimates(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
                  const dn_params *prm, const double *scale, const int32_t *counters,
-                 const double *kfac, const double *e_first, double *est, void *stream);
+                 const double *kfac, const double *e_first, const int64_t *est_off, double *est, void *stream);
 
 /* Outer update, part 1 (nmf.py:575, 148-158): per-sample sums over this rank's genes,
  * sums[0:p] = sum_g x_w, sums[p:2p] = sum over genes with a non-zero DI row of x_w/(1-rho),
