@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdegnorm_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 DN_NCOUNTERS = 8
 DN_MAX_BINS = 64
 DN_MAX_SAMPLES = 256
@@ -45,7 +45,7 @@ _SIGS = {
     "dn_init_ratio_svd": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P, _P,
                                     C.c_int64, _P]),
     "dn_baseline_selection": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), C.POINTER(DnPlan), _P, _P, _P, _P,
-                                        _P, _P, _P, _P, _P, C.c_int64, _P]),
+                                        _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P]),
     "dn_estimates": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(DnParams), _P, _P, _P, _P, _P, _P, _P]),
     "dn_outer_sums": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, _P]),
     "dn_outer_apply": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P]),

@@ -27,41 +27,7 @@ __global__ void __launch_bounds__(256) estimates_kernel(const double *cov, const
         const int ex = counters[(long long)gid * DN_NCOUNTERS + DN_CNT_EXIT];
         const int n0 = counters[(long long)gid * DN_NCOUNTERS + DN_CNT_N_HICOV];
         const double *K = kfac + (long long)gid * p;
-        if (ex == DN_EXIT_FEW_HICOV || ex == DN_EXIT_EMPTY_SAMPLE || ex == DN_EXIT_MEDIAN) {
-            for (int i = 0; i < p; ++i) {
-                const double s = scale[i];
-                for (int j = threadIdx.x; j < L; j += blockDim.x) out[(long long)i * L + j] = F[(long long)i * L + j] / s;
-            }
-        } else if (n0 < L) {
-            for (int j = threadIdx.x; j < L; j += blockDim.x) {
-                double e = -1.0e300;
-                for (int i = 0; i < p; ++i) e = fmax(e, (F[(long long)i * L + j] / scale[i]) / K[i]);
-                for (int i = 0; i < p; ++i) {
-                    const double x = F[(long long)i * L + j] / scale[i];
-                    const double ke = K[i] * e;
-                    out[(long long)i * L + j] = ke < x ? x : ke;
-                }
-            }
-        } else {
-            const double *E0 = e_first + o0;
-            for (int j = threadIdx.x; j < L; j += blockDim.x) {
-                if (ex == DN_EXIT_REFINED) {
-                    double e = -1.0e300;
-                    for (int i = 0; i < p; ++i) e = fmax(e, (F[(long long)i * L + j] / scale[i]) / K[i]);
-                    for (int i = 0; i < p; ++i) out[(long long)i * L + j] = K[i] * e;
-                } else {
-                    const double e = E0[j];
-                    for (int i = 0; i < p; ++i) {
-                        double ke = K[i] * e;
-                        if (ex != DN_EXIT_NO_SELECTION) {
-                            const double x = F[(long long)i * L + j] / scale[i];
-                            ke = ke < x ? x : ke;
-                        }
-                        out[(long long)i * L + j] = ke;
-                    }
-                }
-            }
-        }
+        write_estimate(F, L, p, scale, ex, n0, K, e_first ? e_first + o0 : nullptr, out, threadIdx.x, blockDim.x);
     }
 }
 
@@ -221,7 +187,8 @@ int warps_for_tier(long long cols) {
 int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
                const dn_params *prm, const dn_plan *plan, const double *scale, const int32_t *ds_start,
                const double *row_max, double *row_max_out, double *rho,
-               uint8_t *ran, int32_t *counters, double *kfac, double *e_first, double *est_rowsum, double *cov_rowsum,
+               uint8_t *ran, int32_t *counters, double *kfac, double *e_first, double *est, const int64_t *est_off,
+               double *est_rowsum, double *cov_rowsum,
                void *workspace, int64_t workspace_bytes, void *stream) {
     int rc = check_params(prm);
     if (rc) return rc;
@@ -241,6 +208,7 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     a.rho = rho; a.ran = ran; a.counters = counters; a.kfac = kfac; a.e_first = e_first;
     a.est_rowsum = est_rowsum; a.cov_rowsum = cov_rowsum;
     a.row_max = row_max; a.row_max_out = row_max_out;
+    a.est = est; a.est_off = (const long long *)est_off;
     a.resident_cols = plan->resident_cols;
     a.ld_res = plan->resident_cols;
     // workspace: [queue (256 B)] [per-CTA slabs]
@@ -415,17 +383,20 @@ int dn_init_ratio_svd(const double *cov, const int64_t *off, const int32_t *orde
     if (!est_rowsum || !cov_rowsum) return fail(DN_ERR_INVALID, "null output%s");
     if (plan && plan->tile == 0) return fail(DN_ERR_INVALID, "the init pass needs a plan made with for_init = 1%s");
     return run_kernel(MODE_INIT, cov, off, order, n_work, prm, plan, nullptr, nullptr, nullptr, row_max, nullptr, nullptr,
-                      counters, nullptr, nullptr, est_rowsum, cov_rowsum, workspace, workspace_bytes, stream);
+                      counters, nullptr, nullptr, nullptr, nullptr, est_rowsum, cov_rowsum, workspace, workspace_bytes,
+                      stream);
 }
 
 int dn_baseline_selection(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
                           const dn_params *prm, const dn_plan *plan, const double *scale, const int32_t *ds_start,
                           const double *row_max, double *rho, uint8_t *ran, int32_t *counters, double *kfac,
-                          double *e_first, void *workspace, int64_t workspace_bytes, void *stream) {
+                          double *e_first, double *est, const int64_t *est_off, void *workspace,
+                          int64_t workspace_bytes, void *stream) {
     if (!scale || !rho || !ran) return fail(DN_ERR_INVALID, "null pointer argument%s");
     if (prm && prm->downsample_rate > 1 && !ds_start) return fail(DN_ERR_INVALID, "ds_start required when downsampling%s");
+    if (est && !kfac) return fail(DN_ERR_INVALID, "fused estimates need kfac%s");
     return run_kernel(MODE_BS, cov, off, order, n_work, prm, plan, scale, ds_start, row_max, nullptr, rho, ran, counters,
-                      kfac, e_first, nullptr, nullptr, workspace, workspace_bytes, stream);
+                      kfac, e_first, est, est_off, nullptr, nullptr, workspace, workspace_bytes, stream);
 }
 
 int dn_estimates(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work, const dn_params *prm,

@@ -56,6 +56,8 @@ struct KArgs {
     const double *row_max;  // n x p row maxima of the raw coverage (from the init pass) or NULL
     double *row_max_out;    // init pass: where to write them (or NULL)
     int eig_hint;           // small path: adaptive blind power steps on/off
+    double *est;            // fused estimates of the last outer iteration (or NULL): output buffer ...
+    const long long *est_off;  // ... and the column offset of every gene's block in it (NULL: same as off)
     int nsets;              // tiled path: ceil(Gram tiles / threads); > 1 parks accumulators in global scratch
     long long gacc_doubles; // tiled path: size of that scratch per CTA
 };
@@ -253,6 +255,47 @@ __device__ double median_one_minus(const double *rho, int p) {
         if (rank == k_hi) hi = ai;
     }
     return 0.5 * (lo + hi);
+}
+
+// Full-length estimate of one gene for the last outer iteration (nmf.py:217, 247, 333-337, 343-344, 350-351,
+// 358-365).  Called by every thread that shares the gene: t0 = this thread's index among them, nt = how many.
+// K = |K| floored as the reference does (the kfac output); E0 = E of the first fit (used when no column was filtered).
+__device__ __forceinline__ void write_estimate(const double *F, int L, int p, const double *scale, int ex, int n0,
+                                               const double *K, const double *E0, double *out, int t0, int nt) {
+    if (ex == DN_EXIT_FEW_HICOV || ex == DN_EXIT_EMPTY_SAMPLE || ex == DN_EXIT_MEDIAN || ex < 0) {
+        for (int i = 0; i < p; ++i) {
+            const double s = scale[i];
+            for (int j = t0; j < L; j += nt) out[(long long)i * L + j] = F[(long long)i * L + j] / s;
+        }
+    } else if (n0 < L) {
+        for (int j = t0; j < L; j += nt) {
+            double e = -1.0e300;
+            for (int i = 0; i < p; ++i) e = fmax(e, (F[(long long)i * L + j] / scale[i]) / K[i]);
+            for (int i = 0; i < p; ++i) {
+                const double x = F[(long long)i * L + j] / scale[i];
+                const double ke = K[i] * e;
+                out[(long long)i * L + j] = ke < x ? x : ke;
+            }
+        }
+    } else {
+        for (int j = t0; j < L; j += nt) {
+            if (ex == DN_EXIT_REFINED) {
+                double e = -1.0e300;
+                for (int i = 0; i < p; ++i) e = fmax(e, (F[(long long)i * L + j] / scale[i]) / K[i]);
+                for (int i = 0; i < p; ++i) out[(long long)i * L + j] = K[i] * e;
+            } else {
+                const double e = __ldcg(E0 + j);
+                for (int i = 0; i < p; ++i) {
+                    double ke = K[i] * e;
+                    if (ex != DN_EXIT_NO_SELECTION) {
+                        const double x = F[(long long)i * L + j] / scale[i];
+                        ke = ke < x ? x : ke;
+                    }
+                    out[(long long)i * L + j] = ke;
+                }
+            }
+        }
+    }
 }
 
 }  // namespace

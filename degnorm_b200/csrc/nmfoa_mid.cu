@@ -835,6 +835,11 @@ __global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
             }
         }
         __syncthreads();
+        if (a.est) {
+            write_estimate(F, L, p, g.scale, exit_code, n0, g.K, a.e_first ? a.e_first + o0 : nullptr,
+                           a.est + (long long)p * (a.est_off ? a.est_off[gid] : o0), g.crank * MNT + tid, g.csize * MNT);
+            __syncthreads();
+        }
         cl.sync();
     }
 }

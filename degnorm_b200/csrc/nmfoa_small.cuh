@@ -992,6 +992,12 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
             }
         }
         __syncthreads();
+        if (a.est) {
+            // last outer iteration: the CTA(s) that own the gene write its full-length estimate (fused dn_estimates)
+            write_estimate(F, L, p, g.scale, exit_code, n0, g.K, a.e_first ? a.e_first + o0 : nullptr,
+                           a.est + (long long)p * (a.est_off ? a.est_off[gid] : o0), g.crank * NT + tid, g.csize * NT);
+            __syncthreads();
+        }
         if constexpr (CLU) cg::this_cluster().sync();    // nobody re-uses a peer's ticket slot before it was read
     }
 }

@@ -324,14 +324,13 @@ class ShardEngine(object):
                     _ptr(scale), _ptr(ds_dev[it]) if ds_dev is not None else C.c_void_p(0), _ptr(row_max),
                     _ptr(rho), _ptr(ran[it]), _ptr(counters[it]), _ptr(kfac),
                     _ptr(e_first) if (last and e_first is not None) else C.c_void_p(0),
+                    _ptr(est) if (overlap_est and last) else C.c_void_p(0),
+                    _ptr(self.est_off_dev) if (overlap_est and last) else C.c_void_p(0),
                     _ptr(b.ws), b.ws.numel(), C.c_void_p(b.stream.cuda_stream)))
                 self.launches += 1
                 if overlap_est and last:
-                    # this bucket's estimates, then their trip to the host, behind the bucket's own kernel
-                    check(lib.dn_estimates(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(self.cprm),
-                                           _ptr(scale_used), _ptr(counters[it]), _ptr(kfac), _ptr(e_first),
-                                           _ptr(self.est_off_dev), _ptr(est), C.c_void_p(b.stream.cuda_stream)))
-                    self.launches += 1
+                    # the kernel wrote this bucket's estimates itself (est != NULL): their trip to the host starts as
+                    # soon as the bucket's launch has finished, while the other buckets still compute
                     lo, hi = p * int(b.est_lo), p * int(b.est_hi)
                     with torch.cuda.stream(b.stream):
                         est_host[lo:hi].copy_(est[lo:hi], non_blocking=True)

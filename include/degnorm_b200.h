@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 4
+#define DN_ABI_VERSION 5
 #define DN_MAX_BINS 64      /* baseline-selection bins held in the fused kernel (reference default: 20) */
 #define DN_MAX_SAMPLES 256  /* p supported by the fused kernels (one thread per sample in the n x p steps) */
 #define DN_NCOUNTERS 8      /* int32 counters per gene, see dn_counter */
@@ -130,11 +130,15 @@ int dn_init_ratio_svd(const double *cov, const int64_t *off, const int32_t *orde
  * row_max = row maxima from dn_init_ratio_svd (NULL: every gene is scanned for its maximum).
  * Outputs: rho (n x p, already clipped to [0, 0.9] as nmf.py:398-399), ran (n, uint8),
  * counters (n x DN_NCOUNTERS), kfac (n x p: |K| floored as nmf.py:361-362, input of dn_estimates),
- * e_first (sum_g L_g doubles or NULL: E of the first fit for genes where no column was filtered). */
+ * e_first (sum_g L_g doubles or NULL: E of the first fit for genes where no column was filtered).
+ * est (or NULL): when given (last outer iteration), every gene's full-length estimate is written by the CTA(s) that
+ * just finished the gene, at column offset est_off[g] (NULL: off[g]) -- the fused form of dn_estimates, which lets the
+ * caller start the device-to-host copy of a bucket's estimates as soon as the bucket's launch has finished. */
 int dn_baseline_selection(const double *cov, const int64_t *off, const int32_t *order, int32_t n_work,
                           const dn_params *prm, const dn_plan *plan,
                           const double *scale, const int32_t *ds_start, const double *row_max,
                           double *rho, uint8_t *ran, int32_t *counters, double *kfac, double *e_first,
+                          double *est, const int64_t *est_off,
                           void *workspace, int64_t workspace_bytes, void *stream);
 
 /* Replaces the estimate assembly at nmf.py:217, 247, 333-365 for the last outer iteration: writes the
