@@ -1,4 +1,5 @@
 // degnorm_b200 -- C ABI, host-side planning, and the small n x p / estimate kernels.
+#include <stdlib.h>
 #include "common.cuh"
 #include "launch.h"
 
@@ -229,6 +230,10 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
         if (mode != MODE_BS || P == 0) return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
         a.pp = P;
         a.eig_hint = 1;
+        {
+            const char *e = getenv("DN_EIG_SHARED");       // tuning switch (default: redundant solves)
+            a.eig_shared = e ? atoi(e) : 0;
+        }
         a.ws_stride = small_slab_doubles(P, plan->ws_cols);
         if (P == 4) return dn_launch_small4(a, plan, st);
         if (P == 8) return dn_launch_small8(a, plan, st);

@@ -56,6 +56,7 @@ struct KArgs {
     const double *row_max;  // n x p row maxima of the raw coverage (from the init pass) or NULL
     double *row_max_out;    // init pass: where to write them (or NULL)
     int eig_hint;           // small path: adaptive blind power steps on/off
+    int eig_shared;         // small path, multi-warp CTAs: warp 0 solves alone instead of every warp redundantly
     double *est;            // fused estimates of the last outer iteration (or NULL): output buffer ...
     const long long *est_off;  // ... and the column offset of every gene's block in it (NULL: same as off)
     int nsets;              // tiled path: ceil(Gram tiles / threads); > 1 parks accumulators in global scratch

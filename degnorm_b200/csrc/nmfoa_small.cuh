@@ -424,7 +424,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
 // v: whole vector in registers (in: warm start unless cold; out: unit-norm eigenvector, or 0 for a zero matrix).
 // inv_lam: 1 / lambda_1 from the last checked step; hint: steps the previous solve needed.
 template <int P, int NW>
-__device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[P], bool cold, double &inv_lam, int &hint) {
+__device__ __forceinline__ int eig_small_core(const KArgs &a, SGene &g, double (&v)[P], bool cold, double &inv_lam, int &hint) {
     constexpr int NT = NW * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *vx = g.vx + warp * (2 * P);
@@ -519,7 +519,34 @@ __device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[
     if (ok == 1) {
         if (checked == 1 && d < 0.02 * SMALL_EIG_TOL) hint = steps > 1 ? steps - 1 : 1;
         else hint = steps;
-    } else {                                       // uniform across the CTA (every warp solved the same matrix)
+    }
+    return ok;
+}
+
+// Every warp solves redundantly (no barrier before the next phase A), or -- KArgs.eig_shared, multi-warp CTAs --
+// warp 0 solves alone and hands v over through shared memory (one more barrier, but the other warps' issue slots
+// go to the SM's other CTAs).  The small-gap / distrust fallback is block-wide either way.
+template <int P, int NW>
+__device__ __forceinline__ void eig_small(const KArgs &a, SGene &g, double (&v)[P], bool cold, double &inv_lam, int &hint) {
+    constexpr int NT = NW * 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ok;
+    if (NW > 1 && a.eig_shared) {
+        if (warp == 0) {
+            ok = eig_small_core<P, NW>(a, g, v, cold, inv_lam, hint);
+#pragma unroll
+            for (int k = 0; k < P; ++k)
+                if (lane == k) g.v[k] = v[k];
+            if (lane == 0) g.ibuf[12] = ok;
+        }
+        __syncthreads();
+        ok = g.ibuf[12];
+        if (warp != 0) load_col<P>(g.v, v);
+        __syncthreads();
+    } else {
+        ok = eig_small_core<P, NW>(a, g, v, cold, inv_lam, hint);
+    }
+    if (ok != 1) {                                 // uniform across the CTA (every warp sees the same verdict)
         if constexpr (NW > 1) __syncthreads();
         int s = eig_squaring<NT>(g.G, P, a.p, g.v, g.red, g.B0, g.B0 + P * P, ok == 2);
         g.eig_steps += s;
