@@ -204,15 +204,51 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
         }
         // phase B: warp w sweeps columns w, w + 8, ... of the chunk; lanes own 6 x 8 tiles
         if (tr0 >= 0) {
+            // The four column pairs are fetched in an order rotated by (c0 / 16): in every one of the four load
+            // instructions the lanes whose c0 differ by 16 or 32 doubles (same banks) then read different pairs, so
+            // the loads are bank-conflict free; the accumulator columns are un-rotated when G is built.
+            // Two columns per trip: 14 loads, then 96 FMAs (the shared-load latency is paid once per pair).
+            int cc = warp;
 #pragma unroll 1
-            for (int cc = warp; cc < ncol; cc += MID_WARPS) {
+            for (; cc + MID_WARPS < ncol; cc += 2 * MID_WARPS) {
+                const double *mc = sM + cc * MCS;
+                const double *md = mc + MID_WARPS * MCS;
+                const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
+                const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
+                const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
+                const double2 u0 = *reinterpret_cast<const double2 *>(mc + uo0);
+                const double2 u1 = *reinterpret_cast<const double2 *>(mc + uo1);
+                const double2 u2 = *reinterpret_cast<const double2 *>(mc + uo2);
+                const double2 u3 = *reinterpret_cast<const double2 *>(mc + uo3);
+                const double2 b0 = *reinterpret_cast<const double2 *>(md + tr0);
+                const double2 b1 = *reinterpret_cast<const double2 *>(md + tr0 + 2);
+                const double2 b2 = *reinterpret_cast<const double2 *>(md + tr0 + 4);
+                const double2 w0 = *reinterpret_cast<const double2 *>(md + uo0);
+                const double2 w1 = *reinterpret_cast<const double2 *>(md + uo1);
+                const double2 w2 = *reinterpret_cast<const double2 *>(md + uo2);
+                const double2 w3 = *reinterpret_cast<const double2 *>(md + uo3);
+                {
+                    const double ar[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
+                    const double uc[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
+                }
+                {
+                    const double ar[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
+                    const double uc[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
+#pragma unroll
+                    for (int r = 0; r < 6; ++r)
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
+                }
+            }
+            if (cc < ncol) {
                 const double *mc = sM + cc * MCS;
                 const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
                 const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
                 const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
-                // the four column pairs are fetched in an order rotated by (c0 / 16): in every one of the four load
-                // instructions the lanes whose c0 differ by 16 or 32 doubles (same banks) then read different
-                // pairs, so the loads are bank-conflict free; the accumulator columns are un-rotated when G is built
                 const double2 u0 = *reinterpret_cast<const double2 *>(mc + uo0);
                 const double2 u1 = *reinterpret_cast<const double2 *>(mc + uo1);
                 const double2 u2 = *reinterpret_cast<const double2 *>(mc + uo2);
