@@ -87,6 +87,7 @@ class ShardEngine(object):
         self.serial_buckets = False
         self.prioritise = True
         self.use_clusters = True
+        self.cluster_min_cols = -1        # -1: default (4096 columns at P = 12); 0: clusters right above the tiers
         self.use_mid = True
         self.force_cluster = 0
         self.clusters = (2, 4, 8, 16)
@@ -189,7 +190,14 @@ class ShardEngine(object):
         left = np.ones(n, dtype=bool)
         prev = 0
         if self.p <= 12:
-            tiers = self.small_tiers if self.small_tiers is not None else SMALL_TIERS
+            # the default tier table is written for P = 12 (240 bytes per column); fewer padded samples hold
+            # proportionally more columns in the same shared memory
+            P = 4 if self.p <= 4 else (8 if self.p <= 8 else 12)
+            grow = 240.0 / (8 * (2 * (P + 2) + 2))
+            tiers = self.small_tiers if self.small_tiers is not None else tuple(
+                (int(t * grow) // 2 * 2, w) for t, w in SMALL_TIERS)
+            if self.cluster_min_cols < 0:
+                self.cluster_min_cols = int(4096 * 12 / P)
             for tier, warps in tiers:
                 while tier > prev and self._make_plan(tier, 1, tier, warps=warps).resident_cols == 0:
                     tier -= 8                      # cap the tier at what fits beside this warp count's scratch
@@ -198,6 +206,12 @@ class ShardEngine(object):
                     self.buckets.append(self._bucket(sel, cand, tier, warps=warps))
                     left[sel] = False
                 prev = max(prev, tier)
+            # genes just beyond the largest single-CTA tier may stay on one CTA, streamed from its slab (L2-resident)
+            if self.cluster_min_cols > 0:
+                sel = np.flatnonzero(left & (cand <= self.cluster_min_cols))
+                if len(sel):
+                    self.buckets.append(self._bucket(sel, cand, 0))
+                    left[sel] = False
             # longer genes: one thread-block cluster per gene, columns split over its CTAs' shared memory
             for cl in (self.clusters if self.use_clusters else ()):
                 cap = cl * self._cluster_share_cap(cl)
