@@ -575,7 +575,9 @@ __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P],
         g.tb[col] = t;
         acc[0] += t;
         acc[1] = fma(t, t, acc[1]);
-        double r = 0.0;
+        // max_i ((KE - x)/(x + 1))^2 (nmf.py:280-282): the largest |num|/den is found by cross-multiplication, so
+        // the column costs one division instead of P
+        double bn = 0.0, bd = 1.0;
 #pragma unroll
         for (int i = 0; i < P; ++i) {
             const double ke = v[i] * t;
@@ -583,11 +585,14 @@ __device__ void final_pass_small(const KArgs &a, SGene &g, const double (&v)[P],
             acc[2 + i] += x[i];
             acc[2 + P + i] += kc;
             if (want_res) {
-                const double q = ((first ? ke : kc) - x[i]) / (x[i] + 1.0);
-                r = fmax(r, q * q);
+                const double num = fabs((first ? ke : kc) - x[i]), den = x[i] + 1.0;
+                if (num * bd > bn * den) { bn = num; bd = den; }
             }
         }
-        if (want_res) g.resb[col] = r;
+        if (want_res) {
+            const double q = bn / bd;
+            g.resb[col] = q * q;
+        }
     }
     if (warp == 0) {
 #pragma unroll
