@@ -444,6 +444,7 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
         t += __shfl_xor_sync(0xffffffffu, t, 2);
         double r = 0.0;
         if (col < n) {
+            double bn = 0.0, bd = 1.0;                      // largest |num| / den by cross-multiplication: one division
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 const double ke = vq[i] * t;
@@ -451,10 +452,12 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
                 sF[i] += x[i];
                 sC[i] += kc;
                 if (want_res) {
-                    const double qv = ((first ? ke : kc) - x[i]) / (x[i] + 1.0);
-                    r = fmax(r, qv * qv);
+                    const double num = fabs((first ? ke : kc) - x[i]), den = x[i] + 1.0;
+                    if (num * bd > bn * den) { bn = num; bd = den; }
                 }
             }
+            const double qv = bn / bd;
+            r = qv * qv;
         }
         r = fmax(r, __shfl_xor_sync(0xffffffffu, r, 1));
         r = fmax(r, __shfl_xor_sync(0xffffffffu, r, 2));
