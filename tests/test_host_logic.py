@@ -130,3 +130,45 @@ def test_helper_statics_match_reference_semantics():
     assert GeneNMFOA.shift_bins([[0, 1], [4, 5], [6, 7]], 1) == [[0, 1], [2, 3], [4, 5]]     # nmf.py:160-187
     x = np.array([[0., 1., 10.], [0., 0.5, 2.]])
     assert GeneNMFOA.get_high_coverage_idx(x).tolist() == [2]                                   # strict >, nmf.py:76
+
+
+def test_save_results_writes_the_reference_files(tmp_path):
+    """nmf.py:603-711: degradation_index_scores.csv, adjusted_read_counts.csv, ran_baseline_selection.csv with columns
+    chr, gene, <samples> / iter_k in cov_dat gene order, and one estimated_coverage_matrices_<chr>.pkl per chromosome
+    holding {gene: p x L}.  (Host-side code: runs without a GPU on a hand-filled model.)"""
+    import pickle
+    import pandas as pd
+    from degnorm_b200 import GeneNMFOA
+    m = GeneNMFOA(degnorm_iter=2)
+    with pytest.raises(ValueError):
+        m.save_results([], pd.DataFrame({"chr": [], "gene": []}), output_dir=str(tmp_path))       # not fitted
+    m.genes = ["gB", "gA", "gC"]
+    m.p, m.n_genes, m.fitted = 2, 3, True
+    m.rho = np.array([[0.1, 0.2], [0.0, 0.3], [0.5, 0.9]])
+    m.x_adj = np.array([[10.0, 20.0], [1.0, 2.0], [5.0, 6.0]])
+    m.ran_baseline_selection = np.array([[True, False], [False, False], [True, True]])
+    est = [np.full((2, 3), 1.0), np.full((2, 4), 2.0), np.full((2, 5), 3.0)]
+    manifest = pd.DataFrame({"chr": ["chr2", "chr1", "chr2", "chr9"], "gene": ["gA", "gB", "gC", "gZ"]})
+    with pytest.raises(IOError):
+        m.save_results(est, manifest, output_dir=str(tmp_path / "missing"))
+    with pytest.raises(ValueError):
+        m.save_results(est, manifest.rename(columns={"chr": "chrom"}), output_dir=str(tmp_path))
+    with pytest.raises(ValueError):
+        m.save_results(est, manifest, output_dir=str(tmp_path), sample_ids=["only_one"])
+    m.save_results(est, manifest, output_dir=str(tmp_path), sample_ids=["s1", "s2"])
+    di = pd.read_csv(tmp_path / "degradation_index_scores.csv")
+    assert di.columns.tolist() == ["chr", "gene", "s1", "s2"] and di.gene.tolist() == ["gB", "gA", "gC"]
+    assert di.chr.tolist() == ["chr1", "chr2", "chr2"]
+    np.testing.assert_allclose(di[["s1", "s2"]].values, m.rho)
+    adj = pd.read_csv(tmp_path / "adjusted_read_counts.csv")
+    np.testing.assert_allclose(adj[["s1", "s2"]].values, m.x_adj)
+    ran = pd.read_csv(tmp_path / "ran_baseline_selection.csv")
+    assert ran.columns.tolist() == ["chr", "gene", "iter_0", "iter_1"] and ran.iter_0.tolist() == [True, False, True]
+    with open(tmp_path / "chr2" / "estimated_coverage_matrices_chr2.pkl", "rb") as f:
+        d2 = pickle.load(f)
+    assert sorted(d2) == ["gA", "gC"] and d2["gA"].shape == (2, 4) and d2["gC"][0, 0] == 3.0
+    with open(tmp_path / "chr1" / "estimated_coverage_matrices_chr1.pkl", "rb") as f:
+        assert list(pickle.load(f)) == ["gB"]
+    # default sample ids (nmf.py:639-640)
+    m.save_results(est, manifest, output_dir=str(tmp_path))
+    assert pd.read_csv(tmp_path / "degradation_index_scores.csv").columns.tolist() == ["chr", "gene", "sample_1", "sample_2"]
