@@ -10,9 +10,9 @@
 //     in the 126 MB L2.  lambda = M - x is recovered on load, as in the small-p kernel.
 //   * the CTA (8 warps) walks its columns in 64-column chunks through a 3-stage ring filled by TMA 1-D bulk copies
 //     (cp.async.bulk + one mbarrier per stage; two chunks = 102 KB in flight per SM).  Phase A: 4 lanes per column (12 rows each, two xor-shuffles for t = v.M_j), new M written
-//     in place into the ring stage and to the slab.  Phase B: warp w takes the chunk's columns j = w (mod 8); its
+//     in place into the ring stage and to the slab.  Phase B: warp w takes the 8 columns its own lanes updated; its
 //     lanes own 30 tiles of 6 x 8 Gram entries that cover the upper triangle, operands straight from the stage
-//     (7 LDS.128 per 48 FMAs), accumulators stay in registers for the whole pass.  Two barriers per chunk.
+//     (7 LDS.128 per 48 FMAs), accumulators stay in registers for the whole pass.  One block barrier per chunk.
 //   * per pass the 8 warps' partial Grams are summed by a fixed halving tree through shared memory; a cluster's CTAs
 //     exchange their sums through per-CTA global slots (double-buffered, one cluster barrier per pass) and add them
 //     in rank order, so every CTA holds the bit-identical G and solves redundantly (warp 0, power iteration on G in
@@ -200,7 +200,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
                 st12(sM + cc * MCS + 12 * q4, m);
                 st12(g.M + ((long long)ch * MCH + cc) * MCS + 12 * q4, m);
             }
-            __syncthreads();
+            __syncwarp();        // phase B of this warp only reads the 8 columns its own lanes just wrote
         }
         // phase B: warp w sweeps columns w, w + 8, ... of the chunk; lanes own 6 x 8 tiles
         if (tr0 >= 0) {
@@ -208,11 +208,13 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             // instructions the lanes whose c0 differ by 16 or 32 doubles (same banks) then read different pairs, so
             // the loads are bank-conflict free; the accumulator columns are un-rotated when G is built.
             // Two columns per trip: 14 loads, then 96 FMAs (the shared-load latency is paid once per pair).
-            int cc = warp;
+            // (columns 8 w .. 8 w + 7 of the chunk: the ones this warp updated in phase A, so no block barrier)
+            int cc = warp * (MCH / MID_WARPS);
+            const int cend = min(ncol, cc + MCH / MID_WARPS);
 #pragma unroll 1
-            for (; cc + MID_WARPS < ncol; cc += 2 * MID_WARPS) {
+            for (; cc + 1 < cend; cc += 2) {
                 const double *mc = sM + cc * MCS;
-                const double *md = mc + MID_WARPS * MCS;
+                const double *md = mc + MCS;
                 const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
                 const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
                 const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
@@ -244,7 +246,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
                         for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
                 }
             }
-            if (cc < ncol) {
+            if (cc < cend) {
                 const double *mc = sM + cc * MCS;
                 const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
                 const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
