@@ -104,6 +104,24 @@ def test_against_oracle_across_sample_counts(p, n_genes, kwargs):
     np.testing.assert_array_equal(m.counters[-1, :, 2], want_calls)
 
 
+def test_mixed_lengths_through_the_default_planner_against_oracle():
+    """A length mix that exercises the default planner end to end (resident tiers of every warp count, the
+    single-CTA streamed bucket, down-sampling offsets): DI, adjusted counts, flags and call counts against the oracle."""
+    from degnorm_b200.synth import synth_numpy
+    rng = np.random.default_rng(2026)
+    lengths = np.concatenate([rng.integers(60, 400, size=10), rng.integers(400, 1800, size=8),
+                              rng.integers(1800, 7000, size=5), [9500, 30000]])
+    kwargs = dict(degnorm_iter=2, nmf_iter=20, downsample_rate=2)
+    mats, reads = synth_numpy(len(lengths), 12, 4242, lengths=lengths, jitter=1e-6)
+    m, est = _gpu_run(mats, reads, **kwargs)
+    ref = _oracle(mats, reads, **kwargs)
+    _compare(m, est, ref)
+    np.testing.assert_array_equal(m.counters[-1, :, 2], np.array([t["nmf_calls"] for t in ref["traces"]]))
+    kinds = {(int(b.plan.threads), int(b.plan.resident_cols) > 0, int(b.plan.cluster)) for b in m._engine.buckets}
+    assert any(not res for _, res, _ in kinds) and len({thr for thr, res, _ in kinds if res}) >= 3, kinds
+    assert any(cl > 1 for _, _, cl in kinds), kinds          # the 4,750- and 15,000-column genes get clusters
+
+
 def test_streamed_tier_equals_resident_tier():
     """Same genes through the shared-memory-resident path and the global-slab path: identical decisions,
     DI equal to rounding."""
