@@ -53,6 +53,9 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
                  nmf_iter=nmf_iter, bins=bins, n_jobs=n_jobs, skip_baseline_selection=skip_baseline_selection,
                  random_state=random_state)
     rank, size = c.rank, c.size
+    # one GPU per worker; made current before any communication (NCCL object collectives stage through it)
+    dev = torch.device(device if device is not None else "cuda:%d" % (rank % torch.cuda.device_count()))
+    torch.cuda.set_device(dev)
     if rank == 0:
         genes = list(cov_dat.keys())
         n_genes = len(genes)
@@ -73,8 +76,6 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
     else:
         mine = c.recv_obj(source=0, tag=333 + rank)
     p = mine["p"]
-    n_dev = torch.cuda.device_count()
-    dev = torch.device(device if device is not None else "cuda:%d" % (rank % n_dev))
     with torch.cuda.device(dev):
         flat, offsets = pack_coverage(mine["mats"], p) if len(mine["mats"]) else (torch.zeros(0, dtype=torch.float64),
                                                                                   np.zeros(1, dtype=np.int64))
