@@ -26,7 +26,7 @@ if rank == 0:
     est = single.run(cov, reads)
     assert np.array_equal(out["ran_baseline_selection"], single.ran_baseline_selection)
     d_rho = float(np.abs(out["rho"] - single.rho).max())
-    d_adj = float(np.abs(out["x_adj"] / single.x_adj - 1).max())
+    d_adj = float((np.abs(out["x_adj"] - single.x_adj) / np.maximum(1.0, np.abs(single.x_adj))).max())
     d_est = max(float(np.abs(a - b).max()) for a, b in zip(out["estimates"].values(), est))
     assert d_rho < 1e-11 and d_adj < 1e-11 and d_est < 1e-8, (d_rho, d_adj, d_est)
     print("mpi twin over NCCL, %d ranks: max|dDI| %.2e, max rel d x_adj %.2e, max|d est| %.2e" % (
