@@ -19,7 +19,7 @@ from ._lib import DnParams, DnPlan, check
 RESIDENT_TIERS = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
 # mid-p kernel (13 <= p <= 48): (cluster size, up to this many candidate columns)
 MID_MAX_P = 48
-MID_CLUSTERS = ((1, 4096), (2, 8192), (4, 16384), (8, 49152), (16, 1 << 31))
+MID_CLUSTERS = ((1, 16384), (2, 32768), (4, 65536), (8, 131072), (16, 1 << 31))   # measured sweep: profiles/r01_mid_cluster_sweep.txt
 # small-p kernel (p <= 12): (columns, warps per CTA); the column caps make whole numbers of CTAs fill an SM's 227 KB
 SMALL_TIERS = ((36, 1), (64, 1), (96, 1), (154, 2), (204, 2), (284, 2), (420, 4), (856, 8))
 
@@ -89,6 +89,7 @@ class ShardEngine(object):
         self.use_clusters = True
         self.cluster_min_cols = -1        # -1: default (4096 columns at P = 12); 0: clusters right above the tiers
         self.use_mid = True
+        self.mid_clusters = None
         self.force_cluster = 0
         self.clusters = (2, 4, 8, 16)
         self.stream_clusters = ((4, 65536), (8, 262144))       # (cluster size, up to this many candidate columns)
@@ -234,7 +235,7 @@ class ShardEngine(object):
             return
         if self.p <= MID_MAX_P and self.use_mid:
             # mid-p kernel (13..48 samples): every gene streams from its slab; cluster size follows gene length
-            for cl, cap in MID_CLUSTERS:
+            for cl, cap in (self.mid_clusters or MID_CLUSTERS):
                 sel = np.flatnonzero(left & (cand <= cap))
                 if len(sel):
                     self.buckets.append(self._bucket(sel, cand, 0, cluster=cl))
