@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--force-streamed", action="store_true", help="tuning: every gene through the streamed tier")
     ap.add_argument("--cluster-min", type=int, default=-2, help="tuning: genes up to this many columns stay on one CTA (streamed)")
     ap.add_argument("--mid-clusters", default="", help="tuning: mid-p cluster table as size:max_cols,...")
+    ap.add_argument("--mid-warps", type=int, default=0, help="tuning: warps per CTA of the mid-p kernel (4: two CTAs per SM)")
     ap.add_argument("--max-len", type=int, default=0, help="tuning: clip gene lengths (removes the long-gene tail)")
     ap.add_argument("--tiers", default="", help="small-p tiers as cols:warps,... (tuning)")
     return ap.parse_args()
@@ -250,6 +251,8 @@ def main():
     eng.force_cluster = args.force_cluster
     if args.mid_clusters:
         eng.mid_clusters = tuple(tuple(int(x) for x in t.split(":")) for t in args.mid_clusters.split(","))
+    if args.mid_warps:
+        eng.mid_warps = args.mid_warps
     if args.cluster_min >= -1:
         eng.cluster_min_cols = args.cluster_min
     eng.load(cov, off, reads)

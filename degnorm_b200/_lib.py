@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdegnorm_b200.so")
+# DEGNORM_B200_LIB: tuning aid, another build of the same library (build.py variants); still no fallback
+LIB_PATH = os.environ.get("DEGNORM_B200_LIB") or os.path.join(HERE, "libdegnorm_b200.so")
 
 ABI_VERSION = 5
 DN_NCOUNTERS = 8

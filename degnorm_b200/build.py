@@ -7,13 +7,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SRC = [os.path.join(CSRC, f) for f in ("abi.cu", "nmfoa_tiled.cu", "nmfoa_small_p4.cu", "nmfoa_small_p8.cu",
-                                       "nmfoa_small_p12.cu", "nmfoa_mid.cu")]
-HDR = [os.path.join(CSRC, f) for f in ("common.cuh", "launch.h", "nmfoa_small.cuh")]
-OBJ = os.path.join(HERE, "csrc", "_build")
-OUT = os.path.join(HERE, "libdegnorm_b200.so")
+                                       "nmfoa_small_p12.cu", "nmfoa_mid_w8.cu", "nmfoa_mid_w4.cu")]
+HDR = [os.path.join(CSRC, f) for f in ("common.cuh", "launch.h", "nmfoa_small.cuh", "nmfoa_mid.cuh")]
+# tuning aid: DEGNORM_B200_VARIANT=name with DEGNORM_B200_NVCC_FLAGS="-DMID_FEAT=3" builds libdegnorm_b200.name.so
+# beside the product library (loaded with DEGNORM_B200_LIB=<path>, see _lib.py)
+VARIANT = os.environ.get("DEGNORM_B200_VARIANT", "")
+OBJ = os.path.join(HERE, "csrc", "_build" + ("_" + VARIANT if VARIANT else ""))
+OUT = os.path.join(HERE, "libdegnorm_b200%s.so" % ("." + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include")]
+         "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include")] + os.environ.get("DEGNORM_B200_NVCC_FLAGS", "").split()
 
 
 def needs_build():

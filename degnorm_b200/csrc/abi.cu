@@ -222,7 +222,7 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
         if (mode != MODE_BS || prm->p <= 12 || prm->p > MID_P) return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
         a.pp = MID_P;
         a.ws_stride = mid_slab_doubles(plan->ws_cols);
-        return dn_launch_mid(a, plan, st);
+        return plan->threads == 128 ? dn_launch_mid4(a, plan, st) : dn_launch_mid8(a, plan, st);
     }
     if (plan->tile == 0) {
         // small-p path (baseline selection only)
@@ -282,15 +282,18 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         // ---- mid-p path (13..48 samples): streamed kernel, optional cluster per gene
         int cl = cluster > 1 ? cluster : 1;
         if (cl != 1 && cl != 2 && cl != 4 && cl != 8 && cl != 16) return fail(DN_ERR_INVALID, "cluster must be 1, 2, 4, 8 or 16%s");
+        // warps = 4: two 4-warp CTAs per SM (one CTA's reduction and eigen-solve overlap the other's stream)
+        const int nw = warps == 4 ? 4 : MID_WARPS;
+        const int chunk = mid_chunk(nw);
         long long share = (max_cols + cl - 1) / cl;
-        share = (share + MID_CHUNK - 1) / MID_CHUNK * MID_CHUNK;
+        share = (share + chunk - 1) / chunk * chunk;
         plan->tile = 6;
-        plan->threads = MID_WARPS * 32;
+        plan->threads = nw * 32;
         plan->cluster = cl;
         plan->resident_cols = 0;
-        plan->smem_bytes = (int32_t)(mid_carve().total * 8);
+        plan->smem_bytes = (int32_t)(mid_carve(nw).total * 8);
         plan->ws_cols = share;
-        long long clusters = sm_count / cl;
+        long long clusters = (long long)sm_count * (nw == 4 ? 2 : 1) / cl;
         if (clusters > n_work) clusters = n_work;
         if (clusters < 1) clusters = 1;
         plan->ctas = (int32_t)(clusters * cl);

@@ -103,16 +103,18 @@ __host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols
     return (d + 31) / 32 * 32;
 }
 
-// ---- mid-p kernel (13 <= p <= 48; nmfoa_mid.cu): streamed, CTA-level cp.async ring of 64-column chunks ----------
+// ---- mid-p kernel (13 <= p <= 48; nmfoa_mid.cuh): streamed, CTA-level TMA ring of (8 x warps)-column chunks ------
+// Two instantiations: 8 warps (one CTA per SM, 64-column chunks) and 4 warps (two CTAs per SM, 32-column chunks:
+// one CTA's reduction / eigen-solve / barriers overlap the other CTA's stream).
 constexpr int MID_P = 48;             // samples padded to this
-constexpr int MID_WARPS = 8;
-constexpr int MID_CHUNK = 64;         // columns per ring stage
+constexpr int MID_WARPS = 8;          // default warps per CTA
 constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
 constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
+__host__ __device__ constexpr int mid_chunk(int nw) { return 8 * nw; }   // columns per ring stage
 
 struct MidCarve { long long small, red, binm, alive, ibuf, lw, tab, mbar, G, buf, ring, total; };
 
-__host__ __device__ inline MidCarve mid_carve() {
+__host__ __device__ inline MidCarve mid_carve(int nw) {
     MidCarve c;
     long long o = 0;
     c.small = o; o += (long long)N_SMALL * MID_P;
@@ -123,9 +125,13 @@ __host__ __device__ inline MidCarve mid_carve() {
     c.lw = o;    o += DN_MAX_BINS / 2;
     c.tab = o;   o += 32;
     c.mbar = o;  o += 4;                        // MID_RING mbarriers
-    c.G = o;     o += (long long)MID_P * MID_P;
-    c.buf = o;   o += 4ll * MID_NE;
-    c.ring = o;  o += (long long)MID_RING * 2 * MID_CHUNK * (MID_P + 2);
+    const long long stage = 2ll * mid_chunk(nw) * (MID_P + 2);
+    // 4-warp CTAs (two per SM): G lives in the ring's last stage, which is free between two passes (the ring is
+    // primed with chunks 0 and 1 only) -- the eigen-solve is the only user of G
+    c.G = nw <= 4 ? o + (nw / 2) * (long long)MID_NE + (MID_RING - 1) * stage : o;
+    o += nw <= 4 ? 0 : (long long)MID_P * MID_P;
+    c.buf = o;   o += (nw / 2) * (long long)MID_NE;
+    c.ring = o;  o += (long long)MID_RING * stage;
     c.total = o;
     return c;
 }
@@ -137,7 +143,8 @@ __host__ __device__ inline long long mid_slab_doubles(long long ws_cols) {
 }
 
 // launchers (each defined in its own translation unit)
-int dn_launch_mid(const KArgs &a, const dn_plan *plan, cudaStream_t st);
+int dn_launch_mid8(const KArgs &a, const dn_plan *plan, cudaStream_t st);
+int dn_launch_mid4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_tiled(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_small4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_small8(const KArgs &a, const dn_plan *plan, cudaStream_t st);

@@ -21,6 +21,7 @@
 //     small-p cluster kernels (bins stay contiguous per CTA, drops rotate locally).
 //
 // No tensor cores: fp64 FMA pipe only.
+#pragma once
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "launch.h"
@@ -28,10 +29,14 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+#ifndef MID_NW
+#error "define MID_NW (warps per CTA: 4 or 8) and MID_LAUNCHER before including nmfoa_mid.cuh"
+#endif
+constexpr int MNW = MID_NW;               // warps per CTA (8: one CTA per SM; 4: two CTAs per SM)
 constexpr int MP = MID_P;                 // padded samples
 constexpr int MCS = MID_P + 2;            // column stride (doubles)
-constexpr int MNT = MID_WARPS * 32;       // threads
-constexpr int MCH = MID_CHUNK;            // columns per chunk
+constexpr int MNT = MNW * 32;             // threads
+constexpr int MCH = mid_chunk(MNW);       // columns per chunk (4 lanes per column in phase A)
 constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
 constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
 
@@ -64,6 +69,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 // generic-proxy accesses (ordinary loads / stores, already ordered by a barrier) before async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+// the same for shared memory only (SASS: FENCE.VIEW.ASYNC.S without the MEMBAR.GPU of the full fence)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 struct MGene {
     double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *buf, *ring;
@@ -151,7 +158,9 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             const int st = ch % MID_RING;
             double *dst = g.ring + st * STG;
             const unsigned bytes = MCH * MCS * 8;
-            fence_proxy_async();
+            // (the slab's ordinary stores were fenced by their writers before the pass: only the stage matters here)
+            // (the full fence is a MEMBAR.GPU on the issuing warp, which the other seven then wait for: -2 %)
+            fence_proxy_async_smem();
             mbar_expect_tx(g.mbar + st, with_x ? 2 * bytes : bytes);
             bulk_g2s(dst, g.M + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
             if (with_x) bulk_g2s(dst + MCH * MCS, g.X + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
@@ -209,59 +218,43 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             // the loads are bank-conflict free; the accumulator columns are un-rotated when G is built.
             // Two columns per trip: 14 loads, then 96 FMAs (the shared-load latency is paid once per pair).
             // (columns 8 w .. 8 w + 7 of the chunk: the ones this warp updated in phase A, so no block barrier)
-            int cc = warp * (MCH / MID_WARPS);
-            const int cend = min(ncol, cc + MCH / MID_WARPS);
+            int cc = warp * (MCH / MNW);
+            const int cend = min(ncol, cc + MCH / MNW);
+#define MID_LOADP(S, col)                                                                   \
+    {                                                                                       \
+        const double *mc_ = sM + (col) * MCS;                                               \
+        S##a0 = *reinterpret_cast<const double2 *>(mc_ + tr0);                              \
+        S##a1 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 2);                          \
+        S##a2 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 4);                          \
+        S##u0 = *reinterpret_cast<const double2 *>(mc_ + uo0);                              \
+        S##u1 = *reinterpret_cast<const double2 *>(mc_ + uo1);                              \
+        S##u2 = *reinterpret_cast<const double2 *>(mc_ + uo2);                              \
+        S##u3 = *reinterpret_cast<const double2 *>(mc_ + uo3);                              \
+    }
+#define MID_FMAP(S)                                                                         \
+    {                                                                                       \
+        const double ar_[6] = {S##a0.x, S##a0.y, S##a1.x, S##a1.y, S##a2.x, S##a2.y};       \
+        const double uc_[8] = {S##u0.x, S##u0.y, S##u1.x, S##u1.y, S##u2.x, S##u2.y, S##u3.x, S##u3.y}; \
+        _Pragma("unroll") for (int r = 0; r < 6; ++r)                                       \
+            _Pragma("unroll") for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar_[r], uc_[q], acc[r][q]); \
+    }
+            double2 Aa0, Aa1, Aa2, Au0, Au1, Au2, Au3, Ba0, Ba1, Ba2, Bu0, Bu1, Bu2, Bu3;
+            // Two columns per trip: 14 loads, then 96 FMAs (the shared-load latency is paid once per pair).
+            // (Keeping the next column's operands in flight behind this column's FMAs measured no faster: the
+            // phase is bound by shared-memory wavefronts, 28 per column for the 6 x 8 tiles, not by load latency.)
 #pragma unroll 1
             for (; cc + 1 < cend; cc += 2) {
-                const double *mc = sM + cc * MCS;
-                const double *md = mc + MCS;
-                const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
-                const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
-                const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
-                const double2 u0 = *reinterpret_cast<const double2 *>(mc + uo0);
-                const double2 u1 = *reinterpret_cast<const double2 *>(mc + uo1);
-                const double2 u2 = *reinterpret_cast<const double2 *>(mc + uo2);
-                const double2 u3 = *reinterpret_cast<const double2 *>(mc + uo3);
-                const double2 b0 = *reinterpret_cast<const double2 *>(md + tr0);
-                const double2 b1 = *reinterpret_cast<const double2 *>(md + tr0 + 2);
-                const double2 b2 = *reinterpret_cast<const double2 *>(md + tr0 + 4);
-                const double2 w0 = *reinterpret_cast<const double2 *>(md + uo0);
-                const double2 w1 = *reinterpret_cast<const double2 *>(md + uo1);
-                const double2 w2 = *reinterpret_cast<const double2 *>(md + uo2);
-                const double2 w3 = *reinterpret_cast<const double2 *>(md + uo3);
-                {
-                    const double ar[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
-                    const double uc[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
-                }
-                {
-                    const double ar[6] = {b0.x, b0.y, b1.x, b1.y, b2.x, b2.y};
-                    const double uc[8] = {w0.x, w0.y, w1.x, w1.y, w2.x, w2.y, w3.x, w3.y};
-#pragma unroll
-                    for (int r = 0; r < 6; ++r)
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
-                }
+                MID_LOADP(A, cc);
+                MID_LOADP(B, cc + 1);
+                MID_FMAP(A);
+                MID_FMAP(B);
             }
             if (cc < cend) {
-                const double *mc = sM + cc * MCS;
-                const double2 a0 = *reinterpret_cast<const double2 *>(mc + tr0);
-                const double2 a1 = *reinterpret_cast<const double2 *>(mc + tr0 + 2);
-                const double2 a2 = *reinterpret_cast<const double2 *>(mc + tr0 + 4);
-                const double2 u0 = *reinterpret_cast<const double2 *>(mc + uo0);
-                const double2 u1 = *reinterpret_cast<const double2 *>(mc + uo1);
-                const double2 u2 = *reinterpret_cast<const double2 *>(mc + uo2);
-                const double2 u3 = *reinterpret_cast<const double2 *>(mc + uo3);
-                const double ar[6] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y};
-                const double uc[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
-#pragma unroll
-                for (int r = 0; r < 6; ++r)
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar[r], uc[q], acc[r][q]);
+                MID_LOADP(A, cc);
+                MID_FMAP(A);
             }
+#undef MID_LOADP
+#undef MID_FMAP
         }
     }
     fence_proxy_async();
@@ -273,7 +266,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     }
     // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
     double *mine = g.buf + (long long)(warp & 3) * MNE + lane * 48;
-    for (int half = MID_WARPS / 2; half >= 1; half >>= 1) {
+    for (int half = MNW / 2; half >= 1; half >>= 1) {
         if (warp >= half && warp < 2 * half && lane < MNTILE) {
             double *dst = g.buf + (long long)(warp - half) * MNE + lane * 48;
 #pragma unroll
@@ -335,16 +328,18 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
 }
 
 // ---- top eigenvector of G (MP x MP, shared); same rules as eig_warp in nmfoa_tiled.cu -----------------------------
-// The 48 x 48 mat-vec is spread over 240 threads (thread = row i, k-range of ten), warp 0 combines the partial
+// The 48 x 48 mat-vec is spread over 48 x EKS threads (thread = row i, k-range of EKR), warp 0 combines the partial
 // products, normalises and tests: two barriers per step instead of one warp doing 2 x 48 FMAs and as many shared
 // loads per lane while seven warps wait.
+constexpr int EKS = MNT / MP;                     // k-slices of the mat-vec (5 at 256 threads, 2 at 128)
+constexpr int EKR = (MP + EKS - 1) / EKS;         // entries of v per slice (10 / 24)
 __device__ int eig_mid_block(const double *G, int p, double *v, double *part, int *flag, bool cold) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int i = tid % MP, ks = tid / MP;
-    const int k_lo = ks * 10;
-    double gk[10];
+    const int k_lo = ks * EKR;
+    double gk[EKR];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) gk[j] = (ks < 5 && k_lo + j < MP) ? G[(k_lo + j) * MP + i] : 0.0;
+    for (int j = 0; j < EKR; ++j) gk[j] = (ks < EKS && k_lo + j < MP) ? G[(k_lo + j) * MP + i] : 0.0;
     if (cold) {
         // G.1 (row sums) is the first iterate: start from the ones vector over the real samples
         if (tid < MP) v[tid] = tid < p ? 1.0 : 0.0;
@@ -353,10 +348,10 @@ __device__ int eig_mid_block(const double *G, int p, double *v, double *part, in
     int steps = 0, ok = 0;
     double prev = 1.0e300;
     for (; steps < EIG_FAST_STEPS + 1;) {
-        if (ks < 5) {
+        if (ks < EKS) {
             double y = 0.0;
 #pragma unroll
-            for (int j = 0; j < 10; ++j) y = fma(gk[j], (k_lo + j < MP) ? v[k_lo + j] : 0.0, y);
+            for (int j = 0; j < EKR; ++j) y = fma(gk[j], (k_lo + j < MP) ? v[k_lo + j] : 0.0, y);
             part[ks * MP + i] = y;
         }
         __syncthreads();
@@ -365,7 +360,7 @@ __device__ int eig_mid_block(const double *G, int p, double *v, double *part, in
             const int r0 = lane, r1 = lane + 32;
             double y0 = 0.0, y1 = 0.0;
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
+            for (int q = 0; q < EKS; ++q) {
                 y0 += part[q * MP + r0];
                 if (r1 < MP) y1 += part[q * MP + r1];
             }
@@ -494,12 +489,12 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
     if (tid < 2 * MP) {
         const int which = tid / MP, i = tid - which * MP;
         double s = 0.0;
-        for (int w = 0; w < MID_WARPS; ++w) s += g.buf[(w * 2 + which) * MP + i];
-        g.buf[MID_WARPS * 2 * MP + tid] = s;              // [0, MP): rsF, [MP, 2MP): rsC
+        for (int w = 0; w < MNW; ++w) s += g.buf[(w * 2 + which) * MP + i];
+        g.buf[MNW * 2 * MP + tid] = s;              // [0, MP): rsF, [MP, 2MP): rsC
     }
-    if (tid == 0) { g.buf[MID_WARPS * 2 * MP + 2 * MP] = sum_t_l; g.buf[MID_WARPS * 2 * MP + 2 * MP + 1] = sum_t2_l; }
+    if (tid == 0) { g.buf[MNW * 2 * MP + 2 * MP] = sum_t_l; g.buf[MNW * 2 * MP + 2 * MP + 1] = sum_t2_l; }
     __syncthreads();
-    double *vals = g.buf + MID_WARPS * 2 * MP;            // 2 MP + 2 values
+    double *vals = g.buf + MNW * 2 * MP;            // 2 MP + 2 values
     mclu_allsum(g, vals, 2 * MP + 2, vals);
     const double sum_t = vals[2 * MP], sum_t2 = vals[2 * MP + 1];
     const double sigma = sqrt(sum_t2);
@@ -538,11 +533,11 @@ __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res,
     final_pass_mid(a, g, first, want_res, e_first_g);
 }
 
-__global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
+__global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const KArgs a) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p;
-    const MidCarve cv = mid_carve();
+    const MidCarve cv = mid_carve(MNW);
     MGene g;
     double *sm = smem + cv.small;
     g.v = sm;            g.K = sm + MP;        g.K0 = sm + 2 * MP;   g.rs0 = sm + 3 * MP;   g.rsF = sm + 4 * MP;
@@ -657,7 +652,7 @@ __global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
                 __syncthreads();
                 int pre = running, tot = 0;
 #pragma unroll
-                for (int q = 0; q < MID_WARPS; ++q) {
+                for (int q = 0; q < MNW; ++q) {
                     const int cq = wcount[q];
                     if (q < warp) pre += cq;
                     tot += cq;
@@ -711,7 +706,7 @@ __global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
                 __syncthreads();
                 if (tid < MP) {
                     double s = 0.0;
-                    for (int w2 = 0; w2 < MID_WARPS; ++w2) s += g.buf[w2 * MP + tid];
+                    for (int w2 = 0; w2 < MNW; ++w2) s += g.buf[w2 * MP + tid];
                     g.rs0[tid] = s;
                 }
                 __syncthreads();
@@ -764,7 +759,7 @@ __global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
                     }
                     if (!(rmax > 0.1)) break;
                     ran = 1;
-                    for (int k = warp; k < g.nalive; k += MID_WARPS) {
+                    for (int k = warp; k < g.nalive; k += MNW) {
                         const int wl = g.lw[g.alive[k]];
                         const double *rr = g.resb + mlstart(g, k);
                         double s = 0.0;
@@ -887,7 +882,7 @@ __global__ void __launch_bounds__(MNT, 1) nmfoa_mid_kernel(const KArgs a) {
 
 }  // namespace
 
-int dn_launch_mid(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
+int MID_LAUNCHER(const KArgs &a, const dn_plan *plan, cudaStream_t st) {
     auto kern = nmfoa_mid_kernel;
     DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem_bytes));
     if (plan->cluster > 8) DN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

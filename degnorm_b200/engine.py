@@ -90,6 +90,7 @@ class ShardEngine(object):
         self.cluster_min_cols = -1        # -1: default (4096 columns at P = 12); 0: clusters right above the tiers
         self.use_mid = True
         self.mid_clusters = None
+        self.mid_warps = 0                # 0: 8 warps, one CTA per SM; 4: two 4-warp CTAs per SM
         self.force_cluster = 0
         self.clusters = (2, 4, 8, 16)
         self.stream_clusters = ((4, 65536), (8, 262144))       # (cluster size, up to this many candidate columns)
@@ -186,7 +187,8 @@ class ShardEngine(object):
             cl = self.force_cluster if self.p <= MID_MAX_P else 0
             if 12 < self.p <= MID_MAX_P and not self.use_mid:
                 cl = -1
-            self.buckets.append(self._bucket(np.arange(n), cand, 0 if self.force_streamed else -1, cluster=cl))
+            self.buckets.append(self._bucket(np.arange(n), cand, 0 if self.force_streamed else -1,
+                                             warps=self.mid_warps if 12 < self.p <= MID_MAX_P else 0, cluster=cl))
             return
         left = np.ones(n, dtype=bool)
         prev = 0
@@ -238,7 +240,7 @@ class ShardEngine(object):
             for cl, cap in (self.mid_clusters or MID_CLUSTERS):
                 sel = np.flatnonzero(left & (cand <= cap))
                 if len(sel):
-                    self.buckets.append(self._bucket(sel, cand, 0, cluster=cl))
+                    self.buckets.append(self._bucket(sel, cand, 0, warps=self.mid_warps, cluster=cl))
                     left[sel] = False
             return
         tiled = -1 if self.p <= MID_MAX_P else 0          # (13..48 samples: ask the planner for the tiled kernel)
