@@ -265,11 +265,13 @@ class ShardEngine(object):
         elif self.group is not None:
             torch.distributed.all_reduce(t, group=self.group)
 
-    def run(self, ds_offsets=None, want_estimates=True, est_host=None):
+    def run(self, ds_offsets=None, want_estimates=True, est_host=None, keep_for_estimates=False):
         """ds_offsets: int32 numpy [degnorm_iter, n] (this shard's genes) or None.  Results -> self.out.
         est_host: pinned float64 host tensor of p * sum(L) elements: the estimates are then laid out in WORK order
         (bucket by bucket, self.est_off) and each bucket's block is copied to the host as soon as the bucket has
-        finished its last outer iteration, overlapping the other buckets' compute."""
+        finished its last outer iteration, overlapping the other buckets' compute.
+        keep_for_estimates: no estimate is materialised, but what estimates() needs afterwards is kept (the E row of
+        every gene's first fit: 1/p of the coverage bytes)."""
         prm, p, n, dev, lib = self.prm, self.p, self.n, self.device, self.lib
         f64 = dict(dtype=torch.float64, device=dev)
         main = torch.cuda.current_stream(dev)
@@ -290,7 +292,7 @@ class ShardEngine(object):
         sums_ws = torch.empty(int(lib.dn_sums_workspace_bytes(nn, p)), dtype=torch.uint8, device=dev)
         kfac = torch.zeros((nn, p), **f64)
         row_max = torch.zeros((nn, p), **f64) if self.use_row_max else None
-        want_e_first = want_estimates and prm.downsample_rate == 1 and n > 0
+        want_e_first = (want_estimates or keep_for_estimates) and prm.downsample_rate == 1 and n > 0
         e_first = torch.zeros(int(self.offsets_np[-1]), **f64) if want_e_first else None
         ds_dev = torch.from_numpy(np.ascontiguousarray(ds_offsets, dtype=np.int32)).to(dev) if ds_offsets is not None else None
         est = torch.empty_like(self.cov) if (want_estimates and n > 0 and n_iter > 0) else None
@@ -379,7 +381,36 @@ class ShardEngine(object):
         self.out = dict(rho=rho[:n], rho0=rho0[:n], x_adj=x_adj[:n], x_weighted=x_w[:n], norm_factors=norm,
                         scale_factors=scale, ran=ran[:, :n], counters=counters[:, :n], init_counters=init_counters[:n],
                         est=est, kfac=kfac[:n], scale_used=scale_used, est_in_work_order=overlap_est)
+        self._e_first = e_first
+        self._can_estimate = (want_estimates or keep_for_estimates) and n > 0 and n_iter > 0
         return self.out
+
+    def estimates(self, gene_ids):
+        """Full-length estimates (nmf.py:217, 247, 333-365) of the listed genes of the last run(), materialised on
+        demand: one dn_estimates launch over just those genes into a compact buffer.  Returns (device tensor,
+        column offsets [len(ids) + 1]); gene k's block is est[p * o[k] : p * o[k + 1]] viewed as p x L."""
+        if not getattr(self, "_can_estimate", False):
+            raise ValueError("run(want_estimates=True) or run(keep_for_estimates=True) first")
+        ids = np.asarray(gene_ids, dtype=np.int64).ravel()
+        if len(ids) == 0:
+            return torch.empty(0, dtype=torch.float64, device=self.device), np.zeros(1, dtype=np.int64)
+        if ids.min() < 0 or ids.max() >= self.n or len(np.unique(ids)) != len(ids):
+            raise ValueError("gene ids must be distinct and in [0, n_genes)")
+        p, dev, o = self.p, self.device, self.out
+        sub = np.zeros(len(ids) + 1, dtype=np.int64)
+        np.cumsum(self.lengths[ids], out=sub[1:])
+        est_off = np.zeros(self.n, dtype=np.int64)
+        est_off[ids] = sub[:-1]
+        est = torch.empty(p * int(sub[-1]), dtype=torch.float64, device=dev)
+        order = torch.from_numpy(ids.astype(np.int32)).to(dev)
+        est_off_dev = torch.from_numpy(est_off).to(dev)
+        main = torch.cuda.current_stream(dev)
+        last = self.prm.degnorm_iter - 1
+        check(self.lib.dn_estimates(_ptr(self.cov), _ptr(self.off_dev), _ptr(order), len(ids), C.byref(self.cprm),
+                                    _ptr(o["scale_used"]), _ptr(o["counters"][last]), _ptr(o["kfac"]),
+                                    _ptr(self._e_first), _ptr(est_off_dev), _ptr(est), C.c_void_p(main.cuda_stream)))
+        self.launches += 1
+        return est, sub
 
     # ---------------------------------------------------------------------------------------------------------
     def phase_ms(self):

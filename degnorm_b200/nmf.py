@@ -7,7 +7,9 @@ Differences from the reference that are deliberate and documented in DESIGN.md:
   * n_jobs is accepted and ignored (the GPU owns the gene-level parallelism; joblib threads are gone).
   * the rank-one step is a p x p Gram eigen-solve instead of scipy svds; K >= 0 by convention.
   * extras that do not exist in the reference: `device=`, `return_estimates=` keyword arguments and the
-    `counters` / `timings` attributes.
+    `counters` / `timings` attributes.  return_estimates='lazy' makes run() return a LazyEstimates sequence: the
+    p x L_g estimates stay un-materialised on the device and are computed and copied only for the genes that are
+    indexed (the report and the plots of the CLI touch a handful of genes, __main__.py:292-309).
   * the estimates returned by run() are views into a pinned host buffer owned by this object; a second run()
     on the same object re-uses it (copy what must outlive the next run).
 """
@@ -22,6 +24,50 @@ import torch
 
 from .engine import Params, ShardEngine, draw_offsets
 from .packing import pack_coverage, pinned_buffer, unpack_estimates
+
+
+class LazyEstimates(object):
+    """Sequence of the p x L_g estimated coverage matrices of the last outer iteration (what GeneNMFOA.run
+    returns, nmf.py:601), materialised on demand: indexing gene i (or fetch([i, j, ...])) runs the estimate kernel
+    for just those genes and copies just their blocks to the host.  The coverage stays on the device for as long as
+    this object lives.  Works wherever the reference indexes or iterates the list (save_results included)."""
+
+    def __init__(self, engine, lengths, batch_columns=4_000_000):
+        self._engine = engine
+        self._lengths = np.asarray(lengths, dtype=np.int64)
+        self._batch_columns = int(batch_columns)
+
+    def __len__(self):
+        return len(self._lengths)
+
+    def fetch(self, gene_ids):
+        """List of estimates for the given gene positions (one launch, one device-to-host copy)."""
+        ids = [int(i) + (len(self) if int(i) < 0 else 0) for i in gene_ids]
+        if any(i < 0 or i >= len(self) for i in ids):
+            raise IndexError("gene index out of range")
+        uniq = sorted(set(ids))
+        p = self._engine.p
+        est, o = self._engine.estimates(uniq)
+        host = est.cpu().numpy()
+        where = {g: k for k, g in enumerate(uniq)}
+        return [host[p * o[where[g]]: p * o[where[g] + 1]].reshape(p, -1) for g in ids]
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self.fetch(range(*i.indices(len(self))))
+        return self.fetch([i])[0]
+
+    def __iter__(self):
+        # batches of ~batch_columns columns: one launch and one copy per batch
+        lo, n = 0, len(self)
+        while lo < n:
+            hi, cols = lo, 0
+            while hi < n and (hi == lo or cols + self._lengths[hi] <= self._batch_columns):
+                cols += self._lengths[hi]
+                hi += 1
+            for m in self.fetch(range(lo, hi)):
+                yield m
+            lo = hi
 
 
 class GeneNMFOA(object):
@@ -139,9 +185,11 @@ class GeneNMFOA(object):
             eng.load(cov_dev, offsets, reads_dev)
             ds = draw_offsets(self.n_genes, self._prm)        # also seeds the global numpy stream (nmf.py:556)
             est_host = None
-            if self.return_estimates and self.n_genes > 0 and self.degnorm_iter > 0:
+            lazy = isinstance(self.return_estimates, str) and self.return_estimates == 'lazy'
+            eager = bool(self.return_estimates) and not lazy
+            if eager and self.n_genes > 0 and self.degnorm_iter > 0:
                 est_host = pinned_buffer(flat.numel(), "est", self._host_cache)
-            out = eng.run(ds, want_estimates=self.return_estimates, est_host=est_host)
+            out = eng.run(ds, want_estimates=eager, est_host=est_host, keep_for_estimates=lazy)
             torch.cuda.synchronize(dev)
             t2 = time.perf_counter()
             self.rho = out["rho"].cpu().numpy()
@@ -152,7 +200,9 @@ class GeneNMFOA(object):
             self.ran_baseline_selection = out["ran"].cpu().numpy().T.astype(bool)
             self.counters = out["counters"].cpu().numpy()
             estimates = None
-            if self.return_estimates and out["est"] is not None:
+            if lazy and self.n_genes > 0 and self.degnorm_iter > 0:
+                estimates = LazyEstimates(eng, [m.shape[1] for m in cov_mats])
+            if eager and out["est"] is not None:
                 if out["est_in_work_order"]:
                     # already on the host (copied bucket by bucket behind the last iteration): views in gene order
                     arr, eo, p_ = est_host.numpy(), eng.est_off, self.p
@@ -191,9 +241,15 @@ class GeneNMFOA(object):
         manifest_chroms = gene_df.chr.unique().tolist()
         first_chrom = gene_df.drop_duplicates('gene').set_index('gene').chr
         position = {g: i for i, g in reversed(list(enumerate(self.genes)))}
-        chrom_gene_dict = {chrom: dict() for chrom in manifest_chroms}
+        chrom_genes = {chrom: list() for chrom in manifest_chroms}
         for gene in gene_intersect:
-            chrom_gene_dict[first_chrom[gene]][gene] = estimates[position[gene]]
+            chrom_genes[first_chrom[gene]].append(gene)
+        chrom_gene_dict = dict()
+        for chrom in manifest_chroms:
+            # (a LazyEstimates materialises one chromosome per launch and copy; a list is simply indexed)
+            where = [position[gene] for gene in chrom_genes[chrom]]
+            mats = estimates.fetch(where) if isinstance(estimates, LazyEstimates) else [estimates[k] for k in where]
+            chrom_gene_dict[chrom] = dict(zip(chrom_genes[chrom], mats))
         chrom_gene_dfs = list()
         for chrom in manifest_chroms:
             chrom_dir = os.path.join(output_dir, str(chrom))

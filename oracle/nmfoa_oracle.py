@@ -174,7 +174,12 @@ def baseline_selection(F, prm, ds_start=None, trace=None):
     def fit(cols):
         tr["nmf_calls"] += 1
         tr["sum_cols"] += int(cols.shape[1])
-        return nmf(cols, prm.nmf_iter, prm.rank1)
+        K_, E_ = nmf(cols, prm.nmf_iter, prm.rank1)
+        # smallest factor entry relative to the largest, over all fits: a numerically-zero entry (~1e-15) makes the
+        # reference's exact test `min(rowsum(KE)) == 0` (nmf.py:314) a coin toss decided by rounding noise
+        k_ = np.abs(np.asarray(K_)).ravel()
+        tr["min_rel_K"] = min(tr.get("min_rel_K", 1.0), float(k_.min() / k_.max()) if k_.max() > 0 else 0.0)
+        return K_, E_
 
     K, E = fit(F0)
     K0, E0 = K.copy(), E.copy()

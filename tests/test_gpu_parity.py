@@ -239,3 +239,208 @@ def test_input_errors_match_reference():
         GeneNMFOA(downsample_rate=45).run(cov, np.ones((2, 3)))   # take-every > a gene (nmf.py:479-481)
     with pytest.raises(ValueError):
         GeneNMFOA().save_results([], None)                    # not fitted (nmf.py:623-624)
+
+
+def _engine_outputs(prm, p, flat, off, reads, ds):
+    import torch
+    from degnorm_b200.engine import ShardEngine
+    eng = ShardEngine(prm, p, "cuda:0")
+    eng.load(flat, off, reads)
+    o = eng.run(ds, want_estimates=False)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy().copy() for k, v in o.items() if torch.is_tensor(v)}
+
+
+def _equivariant(a, c, rows, per_iter, scale_want, lengths, tag, well, tol_clean=1e-9, tol_flipped=1e-5, max_flips=0):
+    """Outputs `c` of a run on re-ordered inputs against the re-ordered outputs `a` of the original run, on the
+    well-conditioned genes `well` (boolean, in c's gene order).
+
+    Why only those ("ill-conditioned genes"): a gene with a handful of reads per sample has no
+    dominant rank-one component (top Gram eigenvalues like 22.8, 20.3, 17.9), the 100 NMF-OA iterations then amplify
+    rounding noise to O(0.1) in DI, and the exact test `min(rowsum(KE)) == 0` (nmf.py:314) on a numerically-zero
+    factor entry is a coin toss -- the reference does not reproduce ITSELF on such genes between its two
+    mathematically identical rank-one routes, nor under one ulp of scale-factor noise.  A re-ordering changes the
+    order in which per-sample sums are added, i.e. exactly such noise.
+
+    On the well-conditioned genes a decision (flags, nmf() call sequence, dropped bins) may change in at most
+    `max_flips` gene-iterations (a flipped gene elsewhere moves every gene's scale factors by ~1e-6, enough to turn
+    a decision that sits within 1e-6 of its threshold); all the others must agree to tol_clean when no gene at all
+    flipped, else to tol_flipped."""
+    import os
+    decided = [0, 1, 2, 3, 5, 6]                            # exit, kept columns, nmf() calls, their widths, dropped bins
+    same = (c["ran"] == per_iter(a["ran"])) & \
+        (c["counters"][:, :, decided] == per_iter(a["counters"])[:, :, decided]).all(axis=2)
+    flips = np.argwhere(~same)                              # (iteration, gene position in c)
+    flipped = np.unique(flips[:, 1])
+    well_flips = [(it, g) for it, g in flips if well[g]]
+    keep = np.setdiff1d(np.flatnonzero(well), flipped)
+    tol = tol_clean if len(flips) == 0 else tol_flipped
+    worst = np.abs(c["rho"][keep] - rows(a["rho"])[keep]).max(axis=1)
+    if os.path.isdir("gpurun_out") and (len(flips) or (worst > tol).any()):
+        with open(os.path.join("gpurun_out", "equivariance_%s.txt" % tag), "w") as f:
+            f.write("%d flips (%d on well-conditioned genes), %d well-conditioned genes beyond %.0e\n" % (
+                len(flips), len(well_flips), int((worst > tol).sum()), tol))
+            for it, g in flips:
+                f.write("iter %d gene@%d L=%d well=%d counters here %s there %s rho diff %.3e\n" % (
+                    it, g, lengths[g], well[g], c["counters"][it, g, :7].tolist(),
+                    per_iter(a["counters"])[it, g, :7].tolist(), np.abs(c["rho"][g] - rows(a["rho"])[g]).max()))
+            for k in keep[worst > tol]:
+                f.write("gene@%d L=%d diff %.3e\n  rho here  %s\n  rho there %s\n" % (
+                    k, lengths[k], np.abs(c["rho"][k] - rows(a["rho"])[k]).max(), np.round(c["rho"][k], 5).tolist(),
+                    np.round(rows(a["rho"])[k], 5).tolist()))
+    assert len(well_flips) <= max_flips, "%d gene-iterations of well-conditioned genes decided differently" % len(well_flips)
+    assert len(flips) <= 2e-3 * same.size, "%d of %d gene-iterations decided differently" % (len(flips), same.size)
+    np.testing.assert_allclose(c["rho"][keep], rows(a["rho"])[keep], rtol=0, atol=tol)
+    np.testing.assert_allclose(c["x_adj"][keep], rows(a["x_adj"])[keep], rtol=tol, atol=tol)
+    np.testing.assert_allclose(c["scale_factors"], scale_want, rtol=1e-12 if len(flips) == 0 else tol_flipped, atol=0)
+    return flips
+
+
+def test_full_size_c2_size_independent_properties_and_oracle_spot_check():
+    """BASELINE.json configs[1] at its full size (20,000 genes x 12 samples, take-every 20, 5 x 100 iterations),
+    which the oracle cannot finish: size-independent properties of the path instead --
+      (1) run-to-run determinism (bitwise);
+      (2) identities of the outer update (nmf.py:575-590): x_adj (1 - rho) = x_weighted norm, scale = scale_used
+          norm, median(norm) = 1, 0 <= rho <= 0.9, flags only where baseline selection ran;
+      (3) gene-order equivariance: permuting the genes (with their down-sampling offsets) permutes the rows --
+          exactly after one outer iteration (the initial scale factors are sums of integer counts, so every gene
+          sees bit-identical inputs: no decision may change, DI to 1e-12), and up to the rare noise-decided genes
+          (see _equivariant) after all five;
+      (4) sample-order equivariance after one outer iteration: permuting the samples permutes the columns;
+      (5) the oracle on a length-stratified sample of genes, fed the scale factors the GPU used in the last outer
+          iteration: DI within 1e-6 and identical flags for every gene; identical nmf() call counts and factorised
+          widths for every gene whose decisions are well-posed.
+    Counts carry a 1e-6 relative jitter so that the high-coverage threshold has no exact ties."""
+    import torch
+    from degnorm_b200.engine import Params, draw_offsets
+    from degnorm_b200.synth import CONFIGS, config_lengths, synth_torch
+    from oracle import nmfoa_oracle as orc
+    cfg = CONFIGS["c2"]
+    n, p, rate = cfg["n_genes"], cfg["p"], cfg["downsample_rate"]
+    lengths = config_lengths("c2")
+    flat, off, reads = synth_torch(lengths, p, cfg["seed"], "cuda:0")
+    gen = torch.Generator(device="cuda:0")
+    gen.manual_seed(7)
+    flat.mul_(1.0 + 1.0e-6 * torch.rand(flat.numel(), generator=gen, device="cuda:0", dtype=torch.float64))
+    prm = Params(downsample_rate=rate)
+    prm1 = Params(downsample_rate=rate, degnorm_iter=1)
+    assert prm.degnorm_iter == 5 and prm.nmf_iter == 100
+    ds = draw_offsets(n, prm)
+    a = _engine_outputs(prm, p, flat, off, reads, ds)
+    a1 = _engine_outputs(prm1, p, flat, off, reads, ds[:1])
+    # well-conditioned genes: at least one count per sample and position on average (see _equivariant)
+    csum = torch.cumsum(flat, 0)
+    ends = torch.as_tensor(p * off[1:] - 1, device="cuda:0")
+    tot = csum[ends].cpu().numpy()
+    mean_cov = np.diff(np.concatenate(([0.0], tot))) / (p * lengths)
+    well = mean_cov >= 1.0
+    del csum
+    assert 0.5 < well.mean() < 0.99
+
+    # (1) determinism
+    b = _engine_outputs(prm, p, flat, off, reads, ds)
+    for k in ("rho", "x_adj", "x_weighted", "scale_factors", "ran", "counters"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    del b
+
+    # (2) identities and ranges
+    rho, x_adj, x_w, norm, scale = a["rho"], a["x_adj"], a["x_weighted"], a["norm_factors"], a["scale_factors"]
+    assert rho.shape == (n, p) and rho.min() >= 0.0 and rho.max() <= 0.9
+    np.testing.assert_allclose(x_adj * (1.0 - rho), x_w * norm[None, :], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(scale, a["scale_used"] * norm, rtol=1e-14, atol=0)
+    assert abs(np.median(norm) - 1.0) < 1e-12
+    exits = a["counters"][:, :, 0]
+    default_exit = (exits >= 1) & (exits <= 3)
+    assert not a["ran"][default_exit].any()
+    assert (a["counters"][:, :, 1] <= (lengths[None, :] + rate - 1) // rate).all()
+    assert a["ran"].any() and (exits == 5).any() and (exits == 1).any()          # the workload exercises the paths
+
+    # (3) gene-order equivariance
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(n)
+    off_p = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lengths[perm], out=off_p[1:])
+    flat_p = torch.empty_like(flat)
+    for k, g in enumerate(perm):
+        flat_p[p * off_p[k]: p * off_p[k + 1]] = flat[p * off[g]: p * off[g + 1]]
+    reads_p = reads[torch.as_tensor(perm, device="cuda:0")].contiguous()
+    ds_p = np.ascontiguousarray(ds[:, perm])
+    c1 = _engine_outputs(prm1, p, flat_p, off_p, reads_p, ds_p[:1])
+    flips = _equivariant(a1, c1, lambda m: m[perm], lambda m: m[:, perm], a1["scale_factors"], lengths[perm], "genes_1iter",
+                         np.ones(n, dtype=bool), tol_clean=1e-12)
+    assert len(flips) == 0                                 # every gene, the ill-conditioned ones included
+    c = _engine_outputs(prm, p, flat_p, off_p, reads_p, ds_p)
+    del flat_p
+    _equivariant(a, c, lambda m: m[perm], lambda m: m[:, perm], scale, lengths[perm], "genes", well[perm], max_flips=10)
+    del c
+
+    # (4) sample-order equivariance (one outer iteration)
+    sp = rng.permutation(p)
+    flat_s = torch.empty_like(flat)
+    sp_dev = torch.as_tensor(sp, device="cuda:0")
+    for g in range(n):
+        L = int(lengths[g])
+        flat_s[p * off[g]: p * off[g + 1]].view(p, L).copy_(flat[p * off[g]: p * off[g + 1]].view(p, L)[sp_dev])
+    d1 = _engine_outputs(prm1, p, flat_s, off, reads[:, sp_dev].contiguous(), ds[:1])
+    del flat_s
+    _equivariant(a1, d1, lambda m: m[:, sp], lambda m: m, a1["scale_factors"][sp], lengths, "samples_1iter", well,
+                 max_flips=2)
+
+    # (5) oracle spot check of the last outer iteration on a length-stratified sample
+    order = np.argsort(lengths, kind="stable")
+    pick = order[np.linspace(0, n - 1, 24).astype(int)]
+    oprm = orc.Params(rank1="gram", downsample_rate=rate)
+    last = prm.degnorm_iter - 1
+    di_checked = well_posed = 0
+    for g in pick:
+        L = int(lengths[g])
+        F = flat[p * off[g]: p * off[g + 1]].view(p, L).cpu().numpy()
+        tr = {}
+        r_, _, f_ = orc.baseline_selection(F / a["scale_used"][:, None], oprm, int(ds[last, g]), tr)
+        r_ = np.clip(r_, 0.0, 0.9)
+        assert int(a["counters"][last, g, 1]) == tr["n_hi"], g
+        if well[g] and tr.get("min_rel_K", 1.0) > 1e-9:
+            # (ill-conditioned genes: see _equivariant; everywhere else the decisions and the DI must be the oracle's)
+            well_posed += 1
+            assert bool(a["ran"][last, g]) == bool(f_), g
+            assert int(a["counters"][last, g, 2]) == tr["nmf_calls"], g
+            assert int(a["counters"][last, g, 3]) == tr["sum_cols"], g
+            if r_.max() > 0:                                   # (all-zero rows are replaced by the sample average)
+                np.testing.assert_allclose(rho[g], r_, rtol=0, atol=DI_TOL, err_msg="gene %d" % g)
+                di_checked += 1
+    assert well_posed >= 15 and di_checked >= 10, (well_posed, di_checked)
+
+
+@pytest.mark.parametrize("case", ["run_p4", "run_p4_ds", "run_p12"])
+def test_lazy_estimates_equal_eager_estimates_and_reference(case, tmp_path):
+    """return_estimates='lazy' (SURVEY section 8 row f-2): estimates materialised on demand for the genes that are
+    indexed -- bitwise the eager ones, equal to the reference fixture, and save_results writes identical files."""
+    import filecmp
+    import os
+    import pandas as pd
+    mats, reads, kwargs, ref = load_case(case)
+    m0, est0 = _gpu_run(mats, reads, **kwargs)
+    m1, est1 = _gpu_run(mats, reads, return_estimates='lazy', **kwargs)
+    np.testing.assert_array_equal(m0.rho, m1.rho)
+    assert len(est1) == len(est0) == len(mats)
+    some = [len(mats) - 1, 0, 2, 0]
+    for k, e in zip(some, est1.fetch(some)):
+        np.testing.assert_array_equal(e, est0[k])
+    np.testing.assert_array_equal(est1[-1], est0[-1])
+    for a, b, c in zip(est1, est0, ref["estimates"]):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_allclose(a, c, rtol=1e-6, atol=1e-6)
+    with pytest.raises(IndexError):
+        est1[len(mats)]
+    manifest = pd.DataFrame({"chr": ["chr%d" % (1 + i % 3) for i in range(len(mats))], "gene": m0.genes})
+    for tag, m, est in (("eager", m0, est0), ("lazy", m1, est1)):
+        os.makedirs(str(tmp_path / tag))
+        m.save_results(est, manifest, output_dir=str(tmp_path / tag))
+    cmp = filecmp.dircmp(str(tmp_path / "eager"), str(tmp_path / "lazy"))
+    assert not cmp.left_only and not cmp.right_only
+    for sub in ["."] + sorted(cmp.common_dirs):
+        files = sorted(os.listdir(str(tmp_path / "eager" / sub)))
+        files = [f for f in files if os.path.isfile(str(tmp_path / "eager" / sub / f))]
+        match, mismatch, errors = filecmp.cmpfiles(str(tmp_path / "eager" / sub), str(tmp_path / "lazy" / sub), files,
+                                                   shallow=False)
+        assert not mismatch and not errors and len(match) == len(files), (sub, mismatch, errors)
