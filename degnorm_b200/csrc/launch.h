@@ -4,7 +4,7 @@
 
 // ---- tiled kernel (any p; nmfoa_tiled.cu): shared-memory carve-up ---------------------------------------------
 struct Carve {
-    long long small, red, binm, alive, ibuf, G, ms, xr, lr, resb, tb, total;   // offsets in doubles
+    long long small, red, binm, alive, ibuf, tp, G, ms, xr, lr, resb, tb, total;   // offsets in doubles
 };
 
 __host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, long long ms_doubles, int resident_cols, int ld_res) {
@@ -15,6 +15,10 @@ __host__ __device__ inline Carve carve(int p, int pp, int g_in_smem, long long m
     c.binm = o;  o += DN_MAX_BINS;
     c.alive = o; o += DN_MAX_BINS / 2;
     c.ibuf = o;  o += 16;
+    // phase A's partial dot products (one per thread): their own 256 doubles when G lives in the global slab; when G
+    // is in shared memory they borrow its first 256 entries (G is dead between the eigen-solve and the end of the next
+    // Gram pass, which rewrites every entry; row slices exist only for pp > 24, so G holds at least 576 doubles)
+    c.tp = o;    o += g_in_smem ? 0 : 256;
     c.G = o;     o += g_in_smem ? (long long)pp * pp : 0;
     c.ms = o;    o += ms_doubles;
     c.xr = o;    o += resident_cols > 0 ? (long long)p * ld_res : 0;
@@ -41,16 +45,19 @@ inline Derived derive(int p) {
     if (ch < 32) ch = 32;
     if (ch > d.nt) ch = d.nt;
     d.ch = ch;
-    d.ldm = ch + 1;
+    // M tile: row-major with a padded row (ch + 1) for the 4 x 4 tiles of p <= 64; column-major with an even column
+    // stride (128-bit operand loads) for the 8 x 8 tiles of p > 64
+    d.ldm = d.tr == 8 ? d.pp + 2 : ch + 1;
     d.nsets = (d.ntiles + d.nt - 1) / d.nt;
     d.gacc_doubles = d.nsets > 1 ? ((long long)d.ntiles * d.tr * d.tr + 31) / 32 * 32 : 0;
     int ks = d.nt / d.ntiles;
-    const long long cap = (long long)d.pp * d.ldm / ((long long)d.ntiles * d.tr * d.tr);
+    const long long msd = d.tr == 8 ? (long long)ch * d.ldm : (long long)d.pp * d.ldm;
+    const long long cap = msd / ((long long)d.ntiles * d.tr * d.tr);
     if (ks > cap) ks = (int)cap;
     if (ks < 1) ks = 1;
     d.ks = ks;
     d.g_in_smem = d.pp <= 64;
-    d.ms_doubles = d.pp * d.ldm;
+    d.ms_doubles = (int)msd;
     d.fixed_doubles = carve(p, d.pp, d.g_in_smem, d.ms_doubles, 0, 0).total;
     return d;
 }

@@ -44,6 +44,7 @@ struct Gene {
     int eig_steps;
     int eig_fallbacks;
     double *B0;      // 2 * pp * pp doubles of global scratch for the small-gap eigen fallback
+    double *tp;      // NT partial dot products (phase A row slices)
     double *gacc;    // ntiles * TR * TR doubles of global scratch: Gram accumulators when tiles > threads
 };
 
@@ -132,6 +133,22 @@ __device__ int eig_warp(const double *G, int pp, int p, double *v, bool cold, in
     return steps;
 }
 
+// TR consecutive rows of one column of the M tile.  Column-major tile (8 x 8 Gram tiles): TR / 2 128-bit loads.  A lane's
+// operands for a column are two such runs (its tile's row block and column block), i.e. 2 TR doubles for TR^2 FMAs;
+// with the earlier row-major tile every one of them was a separate 64-bit load and the row blocks of a warp's
+// tiles fell on two bank groups (16-way conflicts).
+template <int TR, bool CM>
+__device__ __forceinline__ void load_rows(const double *blk, int cidx, int ldm, double (&out)[TR]) {
+    if constexpr (CM) {
+        const double2 *q = reinterpret_cast<const double2 *>(blk + cidx * ldm);
+#pragma unroll
+        for (int r = 0; r < TR / 2; ++r) { const double2 t = q[r]; out[2 * r] = t.x; out[2 * r + 1] = t.y; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < TR; ++r) out[r] = blk[r * ldm + cidx];
+    }
+}
+
 // ---- one pass over the current columns: (optional multiplier update) + Gram accumulate -------------------------
 // UPDATE=false: G = x x^T (first rank-one fit of nmf(), nmf.py:88).
 // UPDATE=true : lambda <- max(0, lambda - c (K E - x)), M = x + lambda, G = M M^T (nmf.py:93-98),
@@ -140,6 +157,8 @@ template <int TR, int NT, bool UPDATE>
 __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool tile_ok) {
     const int tid = threadIdx.x;
     const int p = a.p, pp = a.pp, ldm = a.ldm, CH = a.ch, KS = a.ks;
+    constexpr bool CM = TR == 8;                  // column-major M tile (see load_rows); row-major for the 4 x 4 tiles
+    auto mi = [&](int i, int c) { return CM ? c * ldm + i : i * ldm + c; };
     double acc[TR][TR];
 #pragma unroll
     for (int r = 0; r < TR; ++r)
@@ -148,12 +167,21 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
 
     for (int base = 0; base < g.n_cur; base += CH) {
         const int ncol = min(CH, g.n_cur - base);
-        // phase A: one thread per column
+        // phase A.  Small p (chunk as wide as the CTA): one thread per column.  Otherwise the CTA's NT / CH row
+        // slices share a column (thread = column c, slice s; rows s, s + S, ...): the p loads of a column are then
+        // spread over S threads instead of one dependent loop -- at p = 200 the chunk is 32 columns wide and a
+        // single warp walking 2 x 200 strided rows per column left the pass latency-bound on global memory.
+#ifdef TILED_ONE_THREAD_PER_COLUMN
+        const int S = 1;                       // (A/B switch: the previous phase A)
+#else
+        const int S = NT / CH;
+#endif
+        if (S <= 1) {
         if (tid < ncol) {
             const int pc = phys_col(g, base + tid);
             const double *xc = g.X + pc;
             if (!UPDATE) {
-                for (int i = 0; i < p; ++i) g.ms[i * ldm + tid] = xc[i * g.ld];
+                for (int i = 0; i < p; ++i) g.ms[mi(i, tid)] = xc[i * g.ld];
             } else {
                 double *lc = g.Lm + pc;
                 double t = 0.0;
@@ -165,7 +193,49 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
                     l = l - a.c * res;
                     l = l < 0.0 ? 0.0 : l;
                     lc[i * g.ld] = l;
-                    g.ms[i * ldm + tid] = x + l;
+                    g.ms[mi(i, tid)] = x + l;
+                }
+            }
+        }
+        } else {
+            const int c = tid % CH, sl = tid / CH;
+            const bool act = c < ncol && sl < S;
+            const int pc = act ? phys_col(g, base + c) : 0;
+            const double *xc = g.X + pc;
+            if (!UPDATE) {
+                if (act) {
+#pragma unroll 4
+                    for (int i = sl; i < p; i += S) g.ms[mi(i, c)] = xc[(long long)i * g.ld];
+                }
+            } else {
+                double *lc = g.Lm + pc;
+                double tp0 = 0.0, tp1 = 0.0;
+                if (act) {
+                    int i = sl;
+#pragma unroll 2
+                    for (; i + S < p; i += 2 * S) {
+                        tp0 = fma(g.v[i], xc[(long long)i * g.ld] + lc[(long long)i * g.ld], tp0);
+                        tp1 = fma(g.v[i + S], xc[(long long)(i + S) * g.ld] + lc[(long long)(i + S) * g.ld], tp1);
+                    }
+                    if (i < p) tp0 = fma(g.v[i], xc[(long long)i * g.ld] + lc[(long long)i * g.ld], tp0);
+                }
+                // the slices' partial dot products meet in shared memory and are summed in slice order
+                if (sl < S) g.tp[sl * CH + c] = tp0 + tp1;
+                __syncthreads();
+                double t = 0.0;
+                for (int q = 0; q < S; ++q) t += g.tp[q * CH + c];
+                __syncthreads();
+                if (act) {
+#pragma unroll 4
+                    for (int i = sl; i < p; i += S) {
+                        const double x = xc[(long long)i * g.ld];
+                        double l = lc[(long long)i * g.ld];
+                        const double res = g.v[i] * t - x;        // est - x
+                        l = l - a.c * res;
+                        l = l < 0.0 ? 0.0 : l;
+                        lc[(long long)i * g.ld] = l;
+                        g.ms[mi(i, c)] = x + l;
+                    }
                 }
             }
         }
@@ -193,14 +263,12 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
 #pragma unroll
                             for (int q = 0; q < TR; ++q) acc[r][q] = ga[r * TR + q];
                     }
-                    const double *ma = g.ms + (si * TR) * ldm;
-                    const double *mb = g.ms + (sj * TR) * ldm;
+                    const double *ma = g.ms + (CM ? si * TR : si * TR * ldm);
+                    const double *mb = g.ms + (CM ? sj * TR : sj * TR * ldm);
                     for (int cidx = 0; cidx < ncol; ++cidx) {
                         double av[TR], bv[TR];
-#pragma unroll
-                        for (int r = 0; r < TR; ++r) av[r] = ma[r * ldm + cidx];
-#pragma unroll
-                        for (int r = 0; r < TR; ++r) bv[r] = mb[r * ldm + cidx];
+                        load_rows<TR, CM>(ma, cidx, ldm, av);
+                        load_rows<TR, CM>(mb, cidx, ldm, bv);
 #pragma unroll
                         for (int r = 0; r < TR; ++r)
 #pragma unroll
@@ -215,14 +283,12 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
         } else
         // phase B: register-tiled SYRK out of the shared tile
         if (tile_ok) {
-            const double *ma = g.ms + (ti * TR) * ldm;
-            const double *mb = g.ms + (tj * TR) * ldm;
+            const double *ma = g.ms + (CM ? ti * TR : ti * TR * ldm);
+            const double *mb = g.ms + (CM ? tj * TR : tj * TR * ldm);
             for (int cidx = ks; cidx < ncol; cidx += KS) {
                 double av[TR], bv[TR];
-#pragma unroll
-                for (int r = 0; r < TR; ++r) av[r] = ma[r * ldm + cidx];
-#pragma unroll
-                for (int r = 0; r < TR; ++r) bv[r] = mb[r * ldm + cidx];
+                load_rows<TR, CM>(ma, cidx, ldm, av);
+                load_rows<TR, CM>(mb, cidx, ldm, bv);
 #pragma unroll
                 for (int r = 0; r < TR; ++r)
 #pragma unroll
@@ -280,7 +346,11 @@ __device__ void gram_pass(const KArgs &a, Gene &g, int ti, int tj, int ks, bool 
         }
         if (pp > p) {             // the partials overwrote the tile's zero padding rows: restore them
             __syncthreads();
-            for (int e = tid; e < (pp - p) * ldm; e += NT) g.ms[p * ldm + e] = 0.0;
+            if (CM) {
+                for (int e = tid; e < (pp - p) * CH; e += NT) g.ms[(e / (pp - p)) * ldm + p + e % (pp - p)] = 0.0;
+            } else {
+                for (int e = tid; e < (pp - p) * ldm; e += NT) g.ms[p * ldm + e] = 0.0;
+            }
         }
     }
     __syncthreads();
@@ -410,8 +480,10 @@ __device__ void run_nmf(const KArgs &a, Gene &g, bool first, bool want_res, doub
     final_pass<NT>(a, g, first, T > 0, want_res, e_first_g);
 }
 
+// (two CTAs per SM for the 4 x 4 tiles, which the init pass of every p uses: 128 registers, as before the row-slice
+// phase A grew the unconstrained allocation to 246)
 template <int TR, int NT>
-__global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
+__global__ void __launch_bounds__(NT, TR == 4 ? 2 : 1) nmfoa_kernel(const KArgs a) {
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p, pp = a.pp;
@@ -426,6 +498,7 @@ __global__ void __launch_bounds__(NT) nmfoa_kernel(const KArgs a) {
     g.alive = reinterpret_cast<int *>(smem + cv.alive);
     g.ibuf = reinterpret_cast<int *>(smem + cv.ibuf);
     g.ms = smem + cv.ms;
+    g.tp = smem + cv.tp;
     double *slab = a.ws + (long long)blockIdx.x * a.ws_stride;
     g.B0 = slab;
     long long slab_o = 2ll * pp * pp;
