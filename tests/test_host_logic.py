@@ -172,3 +172,45 @@ def test_save_results_writes_the_reference_files(tmp_path):
     # default sample ids (nmf.py:639-640)
     m.save_results(est, manifest, output_dir=str(tmp_path))
     assert pd.read_csv(tmp_path / "degradation_index_scores.csv").columns.tolist() == ["chr", "gene", "sample_1", "sample_2"]
+
+
+def test_lazy_estimates_sequence_protocol_without_a_gpu():
+    """LazyEstimates over a stand-in engine: distinct sorted ids reach the engine once per
+    request, results come back in the order asked (duplicates and negative indices included), slices and iteration
+    batch their requests, out-of-range indices raise IndexError like a list."""
+    import torch
+    from degnorm_b200.nmf import LazyEstimates
+
+    class FakeEngine(object):
+        p = 3
+
+        def __init__(self, lengths):
+            self.lengths = np.asarray(lengths)
+            self.calls = []
+
+        def estimates(self, ids):
+            ids = list(ids)
+            assert ids == sorted(set(ids))
+            self.calls.append(ids)
+            o = np.zeros(len(ids) + 1, dtype=np.int64)
+            np.cumsum(self.lengths[ids], out=o[1:])
+            buf = np.concatenate([np.full(self.p * self.lengths[g], float(g)) for g in ids]) if ids else np.zeros(0)
+            return torch.from_numpy(buf), o
+
+    lengths = [5, 2, 7, 3, 4]
+    eng = FakeEngine(lengths)
+    est = LazyEstimates(eng, lengths, batch_columns=9)
+    assert len(est) == 5
+    got = est.fetch([3, 0, 3, -1])
+    assert eng.calls == [[0, 3, 4]]
+    assert [m.shape for m in got] == [(3, 3), (3, 5), (3, 3), (3, 4)]
+    assert [float(m[0, 0]) for m in got] == [3.0, 0.0, 3.0, 4.0]
+    assert est[2].shape == (3, 7) and float(est[2][1, 1]) == 2.0
+    assert [float(m[0, 0]) for m in est[1:4]] == [1.0, 2.0, 3.0]
+    eng.calls.clear()
+    assert [float(m[0, 0]) for m in est] == [0.0, 1.0, 2.0, 3.0, 4.0]
+    assert eng.calls == [[0, 1], [2], [3, 4]]                 # batches of at most 9 columns (a long gene goes alone)
+    with pytest.raises(IndexError):
+        est[5]
+    with pytest.raises(IndexError):
+        est.fetch([-6])
