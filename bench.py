@@ -39,6 +39,24 @@ UNIT = "genes/s"
 RUN_KW = dict(degnorm_iter=5, nmf_iter=100)
 
 
+def host_memory_allows(nbytes):
+    """True if `nbytes` of pinned host memory (all ranks of this node together) leave half of what is available."""
+    avail = None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+            avail = min(avail, int(lim) - cur) if avail is not None else int(lim) - cur
+    except Exception:
+        pass
+    return avail is None or nbytes <= 0.5 * avail
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,7 +360,10 @@ def main():
 
     # ---- end to end through the drop-in class, host buffers
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not host_memory_allows(2 * cov.numel() * 8 * world):
+        # (every rank pins its coverage and its estimates: 13 GB per rank at C2; never drive the box out of memory)
+        e2e = dict(value=None, unit=UNIT, skipped="pinned host buffers of all ranks would not fit in host memory")
+    elif not args.no_e2e:
         host = torch.empty(cov.numel(), dtype=torch.float64).pin_memory()
         host.copy_(cov)
         torch.cuda.synchronize(dev)
