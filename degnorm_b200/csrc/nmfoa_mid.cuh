@@ -9,8 +9,9 @@
 //     of P + 2 doubles (the shared-memory-friendly layout, so a chunk is one flat copy); small genes simply stay
 //     in the 126 MB L2.  lambda = M - x is recovered on load, as in the small-p kernel.
 //   * the CTA (8 warps) walks its columns in 64-column chunks through a 3-stage ring filled by TMA 1-D bulk copies
-//     (cp.async.bulk + one mbarrier per stage; two chunks = 102 KB in flight per SM).  Phase A: 4 lanes per column (12 rows each, two xor-shuffles for t = v.M_j), new M written
-//     in place into the ring stage and to the slab.  Phase B: warp w takes the 8 columns its own lanes updated; its
+//     (cp.async.bulk + one mbarrier per stage).  Phase A: 4 lanes per column (12 rows each, two xor-shuffles for
+//     t = v.M_j), new M written in place into the ring stage; the stage goes back to the slab as ONE bulk store
+//     (shared -> global) issued after the next chunk barrier.  Phase B: warp w takes the 8 columns its own lanes updated; its
 //     lanes own 30 tiles of 6 x 8 Gram entries that cover the upper triangle, operands straight from the stage
 //     (7 LDS.128 per 48 FMAs), accumulators stay in registers for the whole pass.  One block barrier per chunk.
 //   * per pass the 8 warps' partial Grams are summed by a fixed halving tree through shared memory; a cluster's CTAs
@@ -32,6 +33,13 @@ namespace {
 #ifndef MID_NW
 #error "define MID_NW (warps per CTA: 4 or 8) and MID_LAUNCHER before including nmfoa_mid.cuh"
 #endif
+#ifndef MID_TMA_STORE
+#define MID_TMA_STORE (MID_NW == 8)
+#endif
+// MID_TMA_STORE: the updated M of a chunk goes back to the slab as ONE bulk copy out of the ring stage (issued by
+// one thread after the chunk barrier) instead of six 128-bit stores per thread in phase A.  The kernel is bound by
+// its load/store pipe: on the 8-warp instantiation this took C3 from 0.52 to 0.59 of the HBM roofline; the 4-warp
+// one (32-column chunks, loads only one chunk ahead of their use) measured no gain and keeps per-thread stores.
 constexpr int MNW = MID_NW;               // warps per CTA (8: one CTA per SM; 4: two CTAs per SM)
 constexpr int MP = MID_P;                 // padded samples
 constexpr int MCS = MID_P + 2;            // column stride (doubles)
@@ -71,6 +79,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 // the same for shared memory only (SASS: FENCE.VIEW.ASYNC.S without the MEMBAR.GPU of the full fence)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// shared -> global bulk copy (TMA store), tracked by the issuing thread's bulk async-groups
+__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// global load that bypasses L1 (the slab's M is written by the async proxy when MID_TMA_STORE is on: an L1 line
+// cached by an earlier ordinary load would be stale)
+__device__ __forceinline__ void ld12cg(const double *p, double (&x)[12]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const double2 t = __ldcg(q + i); x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+}
 
 struct MGene {
     double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *buf, *ring;
@@ -176,9 +202,24 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
 #pragma unroll
         for (int q = 0; q < MID_RING - 1; ++q) issue(q, UPDATE);
     }
+    constexpr bool TSTORE = (MID_TMA_STORE != 0) && UPDATE;
+    // TSTORE schedule, at the barrier that opens chunk ch: stage (ch - 1) holds that chunk's final M -> bulk store;
+    // the store of chunk ch - 2 (one chunk old) has finished reading its stage -> that stage takes chunk ch + 1.
+    auto store_back = [&](int ch) {
+        if (tid == 0 && ch >= 0 && ch < nchunk) {
+            const int ncs = min(MCH, n - ch * MCH);
+            bulk_s2g(g.M + (long long)ch * (MCH * MCS), g.ring + (ch % MID_RING) * STG, (unsigned)(ncs * MCS * 8));
+        }
+    };
     for (int ch = 0; ch < nchunk; ++ch) {
         __syncthreads();                                   // everyone is done with stage (ch - 1): refill it
-        issue(ch + MID_RING - 1, UPDATE);
+        if constexpr (TSTORE) {
+            store_back(ch - 1);
+            if (tid == 0) bulk_wait_read<1>();
+            if (ch + 1 >= MID_RING - 1) issue(ch + 1, UPDATE);
+        } else {
+            issue(ch + MID_RING - 1, UPDATE);
+        }
         wait_stage(ch);                                    // chunk ch has landed
         double *sM = g.ring + (ch % MID_RING) * STG;
         const int ncol = min(MCH, n - ch * MCH);
@@ -207,7 +248,8 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
                     m[i] = fma(0.5, w + fabs(w), x[i]);
                 }
                 st12(sM + cc * MCS + 12 * q4, m);
-                st12(g.M + ((long long)ch * MCH + cc) * MCS + 12 * q4, m);
+                if constexpr (TSTORE) fence_proxy_async_smem();      // the stage is read by the bulk store later
+                else st12(g.M + ((long long)ch * MCH + cc) * MCS + 12 * q4, m);
             }
             __syncwarp();        // phase B of this warp only reads the 8 columns its own lanes just wrote
         }
@@ -259,6 +301,10 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     }
     fence_proxy_async();
     __syncthreads();
+    if constexpr (TSTORE) {
+        store_back(nchunk - 1);
+        if (tid == 0) bulk_wait_all();                     // the slab holds the whole new M before anyone reads it
+    }
     g.primed = prime_next;
     if (prime_next) {
 #pragma unroll
@@ -431,7 +477,7 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
         double m[12], x[12];
         double tp = 0.0;
         if (col < n) {
-            ld12(g.M + (long long)col * MCS + 12 * q4, m);
+            ld12cg(g.M + (long long)col * MCS + 12 * q4, m);
             ld12(g.X + (long long)col * MCS + 12 * q4, x);
 #pragma unroll
             for (int i = 0; i < 12; ++i) tp = fma(vq[i], m[i], tp);
