@@ -24,6 +24,25 @@ def partition_bounds(n_genes, size):
     return out
 
 
+def balanced_partition(cost, size):
+    """Genes -> workers by estimated work: longest-processing-time-first greedy on `cost`
+    (p x candidate columns per gene), each gene to the least loaded worker so far.  Returns one ascending index array
+    per worker; results are scattered back by these indices, so gene order stays the caller's.  The reference's
+    contiguous blocks (partition_bounds) follow the annotation order, where one chromosome's long genes can land on
+    one worker; an outer iteration lasts as long as its slowest worker."""
+    import heapq
+    size = max(1, int(size))
+    cost = np.asarray(cost, dtype=np.float64)
+    order = np.argsort(-cost, kind="stable")
+    heap = [(0.0, w) for w in range(size)]
+    owner = np.empty(len(cost), dtype=np.int64)
+    for g in order:
+        load, w = heapq.heappop(heap)
+        owner[g] = w
+        heapq.heappush(heap, (load + cost[g], w))
+    return [np.flatnonzero(owner == w) for w in range(size)]
+
+
 class SoloComm(object):
     rank, size = 0, 1
 

@@ -16,7 +16,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from .distributed import adapt, partition_bounds
+from .distributed import adapt, balanced_partition, partition_bounds
 from .engine import Params, ShardEngine, draw_offsets
 from .nmf import GeneNMFOA
 from .packing import pack_coverage, unpack_estimates
@@ -41,10 +41,12 @@ def _check_input(x, cov_mats, n_genes, prm):
 
 def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate=1, min_high_coverage=50,
                        nmf_iter=100, bins=20, n_jobs=1, skip_baseline_selection=False, random_state=123,
-                       device=None, return_estimates=True):
+                       device=None, return_estimates=True, partition='balanced'):
     """Same contract as nmf_mpi.py:555-863.  `comm`: an mpi4py communicator (as degnorm_mpi passes), a
     torch.distributed group, or None.  Rank 0's cov_dat / reads_dat are authoritative.  Returns on rank 0
-    {'estimates': OrderedDict gene -> p x L_g, 'rho', 'x_adj', 'ran_baseline_selection'}; None elsewhere."""
+    {'estimates': OrderedDict gene -> p x L_g, 'rho', 'x_adj', 'ran_baseline_selection'}; None elsewhere.
+    partition: 'balanced' (genes to workers by estimated work, results scattered back into cov_dat order) or
+    'contiguous' (the reference's blocks, nmf_mpi.py:605-606)."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError("degnorm_b200 needs a CUDA device (B200); there is no CPU fallback")
@@ -63,16 +65,22 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
         mats = list(cov_dat.values())
         p = _check_input(x, mats, n_genes, prm)
         ds = draw_offsets(n_genes, prm)                     # seeds the global numpy stream (nmf.py:556)
-        bounds = partition_bounds(n_genes, size)
+        if partition == 'contiguous':
+            shards = [np.arange(lo, hi) for lo, hi in partition_bounds(n_genes, size)]
+        elif partition == 'balanced':
+            li = np.array([m.shape[1] for m in mats], dtype=np.int64)
+            shards = balanced_partition(p * ((li + prm.downsample_rate - 1) // prm.downsample_rate), size)
+        else:
+            raise ValueError("partition must be 'balanced' or 'contiguous'")
+
+        def shard(idx):
+            return dict(p=p, mats=[mats[g] for g in idx], reads=x[idx], ds=None if ds is None else ds[:, idx])
         for w in range(size):
-            lo, hi = bounds[w]
             logging.info('(%d/%d) -- %s will be responsible for %d genes.', rank + 1, size,
-                         'host' if w == 0 else 'worker node %d' % w, hi - lo)
+                         'host' if w == 0 else 'worker node %d' % w, len(shards[w]))
             if w > 0:
-                c.send_obj(dict(p=p, mats=mats[lo:hi], reads=x[lo:hi], ds=None if ds is None else ds[:, lo:hi]),
-                           dest=w, tag=333 + w)
-        lo, hi = bounds[0]
-        mine = dict(p=p, mats=mats[lo:hi], reads=x[lo:hi], ds=None if ds is None else ds[:, lo:hi])
+                c.send_obj(shard(shards[w]), dest=w, tag=333 + w)
+        mine = shard(shards[0])
     else:
         mine = c.recv_obj(source=0, tag=333 + rank)
     p = mine["p"]
@@ -88,24 +96,29 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
                     ran=out["ran"].cpu().numpy().T.astype(bool), est=None)
         if return_estimates and out["est"] is not None:
             part["est"] = [np.array(m) for m in unpack_estimates(out["est"], offsets, p)]
-    # star gather of the n x p results (and the last iteration's estimates), rank order = gene order (:809-815)
+    # star gather of the n x p results (and the last iteration's estimates) through rank 0 (:809-815)
     if rank > 0:
         c.send_obj(part, dest=0, tag=666 + rank)
         c.barrier()
         return None
     parts = [part] + [c.recv_obj(source=w, tag=666 + w) for w in range(1, size)]
     c.barrier()
-    keep = [q for q in parts if q["rho"].shape[0] > 0]
+    # scatter the workers' rows back into cov_dat order
+    rho = np.zeros((n_genes, p))
+    x_adj = np.zeros((n_genes, p))
+    ran = np.zeros((n_genes, prm.degnorm_iter), dtype=bool)
+    est_list = [None] * n_genes
+    for idx, q in zip(shards, parts):
+        if len(idx) == 0:
+            continue
+        rho[idx], x_adj[idx], ran[idx] = q["rho"], q["x_adj"], q["ran"]
+        if return_estimates and q["est"] is not None:
+            for g, m in zip(idx, q["est"]):
+                est_list[g] = m
     estimates = None
     if return_estimates:
-        estimates = OrderedDict()
-        flat_est = [m for q in keep for m in (q["est"] or [])]
-        for gname, m in zip(genes, flat_est):
-            estimates[gname] = m
-    return {'estimates': estimates,
-            'rho': np.vstack([q["rho"] for q in keep]),
-            'x_adj': np.vstack([q["x_adj"] for q in keep]),
-            'ran_baseline_selection': np.vstack([q["ran"] for q in keep])}
+        estimates = OrderedDict(zip(genes, est_list))
+    return {'estimates': estimates, 'rho': rho, 'x_adj': x_adj, 'ran_baseline_selection': ran}
 
 
 def save_results(gene_manifest_df, estimates, rho, x_adj, ran_baseline_selection, sample_ids, output_dir):

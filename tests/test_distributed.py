@@ -104,6 +104,25 @@ def _gloo_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def test_balanced_partition_covers_every_gene_once_and_levels_the_load():
+    """genes to workers by estimated work instead of the reference's contiguous blocks."""
+    from degnorm_b200.distributed import balanced_partition, partition_bounds
+    rng = np.random.default_rng(3)
+    for n, size in ((0, 3), (1, 4), (7, 2), (1000, 8), (5000, 3)):
+        cost = np.sort(np.exp(rng.normal(8.0, 0.9, size=n)))[::-1].copy()       # annotation order: long genes first
+        shards = balanced_partition(cost, size)
+        assert len(shards) == size
+        allg = np.concatenate(shards) if n else np.zeros(0, dtype=np.int64)
+        assert sorted(allg.tolist()) == list(range(n))
+        assert all((np.diff(s) > 0).all() for s in shards)                       # ascending: gene order is kept
+        if n >= size:
+            loads = np.array([cost[s].sum() for s in shards])
+            assert loads.max() <= cost.sum() / size + cost.max() + 1e-9           # the greedy bound
+            contiguous = np.array([cost[lo:hi].sum() for lo, hi in partition_bounds(n, size)])
+            assert loads.max() <= contiguous.max() + 1e-9
+    assert [s.tolist() for s in balanced_partition([5, 1, 4, 2], 2)] == [[0, 1], [2, 3]]
+
+
 def test_gloo_two_workers_equal_one():
     import torch.multiprocessing as mp
     from degnorm_b200.synth import synth_numpy
@@ -130,7 +149,7 @@ def test_gloo_two_workers_equal_one():
 
 
 # ------------------------------------------------------------------------------------------------ GPU
-def _gpu_worker(rank, world, port, q):
+def _gpu_worker(rank, world, port, q, partition):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -141,7 +160,8 @@ def _gpu_worker(rank, world, port, q):
         kw = dict(degnorm_iter=2, nmf_iter=30, downsample_rate=3)
         mats, reads = synth_numpy(7, 4, 5, lengths=np.array([300, 420, 700, 256, 512, 900, 333]), jitter=1e-6)
         cov = OrderedDict(("g%d" % i, m) for i, m in enumerate(mats))
-        out = run_gene_nmfoa_mpi(dist.group.WORLD, cov if rank == 0 else OrderedDict(), reads, device="cuda:0", **kw)
+        out = run_gene_nmfoa_mpi(dist.group.WORLD, cov if rank == 0 else OrderedDict(), reads, device="cuda:0",
+                                 partition=partition, **kw)
         q.put((rank, None if out is None else {k: (v if k != "estimates" else list(v.values())) for k, v in out.items()}))
     except Exception as exc:                                   # surface the failure instead of a silent time-out
         import traceback
@@ -151,7 +171,8 @@ def _gpu_worker(rank, world, port, q):
 
 
 @pytest.mark.gpu
-def test_two_processes_on_one_gpu_equal_single_process():
+@pytest.mark.parametrize("partition", ["balanced", "contiguous"])
+def test_two_processes_on_one_gpu_equal_single_process(partition):
     import torch.multiprocessing as mp
     from degnorm_b200 import GeneNMFOA, run_gene_nmfoa_mpi
     from degnorm_b200.synth import synth_numpy
@@ -185,7 +206,7 @@ def test_two_processes_on_one_gpu_equal_single_process():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q, partition)) for r in range(2)]
     for pr in procs:
         pr.start()
     got = dict(q.get(timeout=240) for _ in procs)
