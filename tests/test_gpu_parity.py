@@ -444,3 +444,20 @@ def test_lazy_estimates_equal_eager_estimates_and_reference(case, tmp_path):
         match, mismatch, errors = filecmp.cmpfiles(str(tmp_path / "eager" / sub), str(tmp_path / "lazy" / sub), files,
                                                    shallow=False)
         assert not mismatch and not errors and len(match) == len(files), (sub, mismatch, errors)
+
+
+def test_gene_filter_on_the_device_equals_the_host_filter():
+    """degnorm_b200.gene_filter: the per-gene maxima from one segmented reduction over the
+    packed buffer on the GPU give the same kept set as the host pass, on a C1-shaped workload."""
+    import torch
+    from degnorm_b200.gene_filter import gene_max_coverage, keep_mask
+    from degnorm_b200.synth import config_lengths, synth_torch
+    lengths = config_lengths("c1")
+    flat, off, _ = synth_torch(lengths, 4, 99, "cuda:0")
+    host = flat.cpu()
+    mx_dev = gene_max_coverage(flat, off, 4).cpu().numpy()
+    want = np.array([host[4 * off[g]: 4 * off[g + 1]].max().item() for g in range(len(lengths))])
+    np.testing.assert_array_equal(mx_dev, want)
+    for minimax, rate in ((0, 1), (20, 1), (50, 300)):
+        np.testing.assert_array_equal(keep_mask(flat, off, 4, minimax, rate), keep_mask(host, off, 4, minimax, rate))
+        np.testing.assert_array_equal(keep_mask(flat, off, 4, minimax, rate), ~((want < minimax) | (lengths <= rate)))

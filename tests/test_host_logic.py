@@ -214,3 +214,50 @@ def test_lazy_estimates_sequence_protocol_without_a_gpu():
         est[5]
     with pytest.raises(IndexError):
         est.fetch([-6])
+
+
+def _filter_case(seed=0):
+    import pandas as pd
+    from collections import OrderedDict
+    rng = np.random.default_rng(seed)
+    lengths = [40, 7, 120, 20, 300, 21, 64]
+    peak = [30, 500, 4, 80, 9, 12, 10]
+    buf = np.zeros(3 * sum(lengths))
+    cov, at = OrderedDict(), 0
+    for k, (L, m) in enumerate(zip(lengths, peak)):
+        v = buf[at:at + 3 * L].reshape(3, L)
+        at += 3 * L
+        v[...] = rng.integers(0, m, size=(3, L))
+        v[rng.integers(3), rng.integers(L)] = m
+        cov["g%d" % k] = v
+    genes_df = pd.DataFrame({"chr": "chr1", "gene": list(cov.keys()), "gene_start": 1, "gene_end": lengths})
+    reads = pd.DataFrame({"chr": "chr1", "gene": list(cov.keys()), "s1": 1.0, "s2": 2.0, "s3": 3.0})
+    return cov, genes_df, reads
+
+
+def test_gene_filter_equals_the_reference_loop():
+    """degnorm_b200.gene_filter against a literal restatement of __main__.py:221-244."""
+    from collections import OrderedDict
+    from degnorm_b200.gene_filter import filter_genes
+    for minimax, rate in ((0, 1), (10, 1), (10, 20), (81, 6), (13, 21)):
+        cov, genes_df, reads = _filter_case()
+        want_cov = OrderedDict((g, m) for g, m in cov.items())
+        delete_idx = []
+        for i in range(genes_df.shape[0]):
+            gene = genes_df.gene.iloc[i]
+            cov_mat = want_cov[gene]
+            if (cov_mat.max() < minimax) or (cov_mat.shape[1] <= rate):
+                delete_idx.append(i)
+                del want_cov[gene]
+        want_genes = genes_df.drop(delete_idx, axis=0).reset_index(drop=True)
+        want_reads = reads.drop(delete_idx, axis=0).reset_index(drop=True)
+        got_cov, got_genes, got_reads = filter_genes(cov, genes_df, reads, minimax, rate)
+        assert got_cov is cov and list(got_cov.keys()) == list(want_cov.keys())
+        assert got_genes.equals(want_genes) and got_reads.equals(want_reads)
+    cov, genes_df, reads = _filter_case()
+    with pytest.raises(ValueError, match="No genes available"):
+        filter_genes(cov, genes_df, reads, minimax_coverage=10 ** 6)
+    cov, genes_df, reads = _filter_case()
+    with pytest.raises(ValueError, match="Number of coverage matrices"):
+        cov["extra"] = np.ones((3, 50))
+        filter_genes(cov, genes_df, reads, minimax_coverage=0)
