@@ -397,7 +397,7 @@ def main():
     if rank == 0:
         clock_summary = clocks.summary()
         cb = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:            # (the CPU baseline is an N = 1 figure)
             cb = run_cpu_baseline(cfg, kw, args.cpu_genes or 2 * cores, cores)
         emit(dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                               ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
