@@ -157,6 +157,17 @@ class GeneNMFOA(object):
         if not all(m.shape[0] == self.p for m in cov_mats):
             raise ValueError('Not all coverage matrices have the same number of samples (rows)!')
 
+    def _check_resident(self, cov):
+        """check_input (nmf.py:455-481) for coverage that is already packed on the device."""
+        if self.x.shape[0] != self.n_genes:
+            raise ValueError('Number of genes in read count matrix not equal to number of coverage matrices!')
+        if np.sum(cov.lengths / self.p < 1) > 0:
+            logging.warning('At least one coverage matrix is taller than it is wide.'
+                            'Ensure that coverage matrices are shaped (p x L_i).')
+        if self.downsample_rate > 1:
+            if not np.min(cov.lengths) >= self.downsample_rate:
+                raise ValueError('downsample_rate is too large; take-every size > at least one gene.')
+
     # ---- the hot path ---------------------------------------------------------------------------------------------
     def run(self, cov_dat, reads_dat):
         """GeneNMFOA.run (nmf.py:483-601): returns the list of estimated coverage matrices (p x L_g, cov_dat key
@@ -165,19 +176,35 @@ class GeneNMFOA(object):
         if not torch.cuda.is_available():
             raise RuntimeError("degnorm_b200 needs a CUDA device (B200); there is no CPU fallback")
         t0 = time.perf_counter()
+        from .gene_filter import DeviceCoverage
+        resident = cov_dat if isinstance(cov_dat, DeviceCoverage) else None
         self.n_genes = len(cov_dat)
         self.genes = list(cov_dat.keys())
         self.x = np.copy(reads_dat)
-        cov_mats = list(cov_dat.values())
-        self.p = cov_mats[0].shape[0]
+        if resident is None:
+            cov_mats = list(cov_dat.values())
+            self.p = cov_mats[0].shape[0]
+            gene_lengths = [m.shape[1] for m in cov_mats]
+            nbytes = np.sum([m.nbytes for m in cov_mats])
+        else:
+            # coverage already packed and on the device (gene_filter.DeviceCoverage): no packing, no upload
+            self.p = resident.p
+            gene_lengths = resident.lengths.tolist()
+            nbytes = 8.0 * resident.flat.numel()
         self.ran_baseline_selection = np.zeros(shape=[self.n_genes, self.degnorm_iter]).astype(bool)
-        self.check_input(cov_mats)
-        mem_splits = int(np.ceil(np.sum([m.nbytes for m in cov_mats]) / 5e7))
+        if resident is None:
+            self.check_input(cov_mats)
+        else:
+            self._check_resident(resident)
+        mem_splits = int(np.ceil(nbytes / 5e7))
         self.mem_splits = max(mem_splits, self.n_jobs)
 
         dev = torch.device(self.device if self.device is not None else "cuda:%d" % torch.cuda.current_device())
         with torch.cuda.device(dev):
-            flat, offsets = pack_coverage(cov_mats, self.p, cache=self._host_cache)     # pinned host staging
+            if resident is None:
+                flat, offsets = pack_coverage(cov_mats, self.p, cache=self._host_cache)     # pinned host staging
+            else:
+                flat, offsets = resident.flat, resident.offsets
             t1 = time.perf_counter()
             cov_dev = flat.to(dev, non_blocking=True)
             reads_dev = torch.from_numpy(np.ascontiguousarray(self.x, dtype=np.float64)).to(dev)
@@ -201,13 +228,13 @@ class GeneNMFOA(object):
             self.counters = out["counters"].cpu().numpy()
             estimates = None
             if lazy and self.n_genes > 0 and self.degnorm_iter > 0:
-                estimates = LazyEstimates(eng, [m.shape[1] for m in cov_mats])
+                estimates = LazyEstimates(eng, gene_lengths)
             if eager and out["est"] is not None:
                 if out["est_in_work_order"]:
                     # already on the host (copied bucket by bucket behind the last iteration): views in gene order
                     arr, eo, p_ = est_host.numpy(), eng.est_off, self.p
-                    estimates = [arr[p_ * int(eo[g]): p_ * (int(eo[g]) + m.shape[1])].reshape(p_, -1)
-                                 for g, m in enumerate(cov_mats)]
+                    estimates = [arr[p_ * int(eo[g]): p_ * (int(eo[g]) + L)].reshape(p_, -1)
+                                 for g, L in enumerate(gene_lengths)]
                 else:
                     estimates = unpack_estimates(out["est"], offsets, self.p, cache=self._host_cache)
             t3 = time.perf_counter()

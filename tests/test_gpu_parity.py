@@ -461,3 +461,46 @@ def test_gene_filter_on_the_device_equals_the_host_filter():
     for minimax, rate in ((0, 1), (20, 1), (50, 300)):
         np.testing.assert_array_equal(keep_mask(flat, off, 4, minimax, rate), keep_mask(host, off, 4, minimax, rate))
         np.testing.assert_array_equal(keep_mask(flat, off, 4, minimax, rate), ~((want < minimax) | (lengths <= rate)))
+
+
+def test_resident_coverage_handle_equals_the_dictionary_path():
+    """gene_filter.DeviceCoverage: one upload shared by the gene filter and GeneNMFOA.run.  Same outputs as the
+    dictionary path (bitwise: the kernels see the same packed buffer) and as the reference fixture; the filtered
+    handle equals running on the filtered dictionary."""
+    from collections import OrderedDict as OD
+    import pandas as pd
+    from degnorm_b200 import GeneNMFOA
+    from degnorm_b200.gene_filter import DeviceCoverage, filter_genes
+    mats, reads, kwargs, ref = load_case("run_p4")
+    cov = OD(("g%d" % i, x) for i, x in enumerate(mats))
+    m0 = GeneNMFOA(**kwargs)
+    est0 = m0.run(cov, reads)
+    dc = DeviceCoverage(cov, device="cuda:0")
+    m1 = GeneNMFOA(**kwargs)
+    est1 = m1.run(dc, reads)
+    _compare(m1, est1, ref)
+    np.testing.assert_array_equal(m1.rho, m0.rho)
+    np.testing.assert_array_equal(m1.x_adj, m0.x_adj)
+    for a, b in zip(est1, est0):
+        np.testing.assert_array_equal(a, b)
+    lazy = GeneNMFOA(return_estimates='lazy', **kwargs).run(dc, reads)
+    np.testing.assert_array_equal(lazy[1], est0[1])
+    # filter on the device, then run: equals the host filter followed by the dictionary path
+    genes_df = pd.DataFrame({"chr": "chr1", "gene": list(cov.keys())})
+    reads_df = pd.DataFrame(reads, columns=["s%d" % i for i in range(reads.shape[1])])
+    reads_df.insert(0, "gene", list(cov.keys()))
+    reads_df.insert(0, "chr", "chr1")
+    thr = float(np.median([x.max() for x in mats]))
+    dc2, g2, r2 = dc.filter(genes_df, reads_df, minimax_coverage=thr, downsample_rate=1)
+    cov_h, g_h, r_h = filter_genes(OD(cov), genes_df, reads_df, minimax_coverage=thr, downsample_rate=1)
+    assert 0 < len(dc2) < len(cov) and dc2.keys() == list(cov_h.keys()) and g2.equals(g_h) and r2.equals(r_h)
+    cols = list(reads_df.columns[2:])
+    ma = GeneNMFOA(**kwargs)
+    ea = ma.run(dc2, r2[cols].values)
+    mb = GeneNMFOA(**kwargs)
+    eb = mb.run(cov_h, r_h[cols].values)
+    np.testing.assert_array_equal(ma.rho, mb.rho)
+    np.testing.assert_array_equal(ma.ran_baseline_selection, mb.ran_baseline_selection)
+    for a, b in zip(ea, eb):
+        np.testing.assert_array_equal(a, b)
+    assert ma.genes == list(cov_h.keys())

@@ -261,3 +261,28 @@ def test_gene_filter_equals_the_reference_loop():
     with pytest.raises(ValueError, match="Number of coverage matrices"):
         cov["extra"] = np.ones((3, 50))
         filter_genes(cov, genes_df, reads, minimax_coverage=0)
+
+
+def test_device_coverage_handle_filters_like_filter_genes_on_host_tensors():
+    """gene_filter.DeviceCoverage with host tensors (the same code runs on the device): packing, select (runs of
+    kept genes), filter against filter_genes, round trip to the reference's dictionary."""
+    from degnorm_b200.gene_filter import DeviceCoverage, filter_genes
+    for minimax, rate in ((0, 1), (10, 1), (10, 20), (81, 6), (13, 21)):
+        cov, genes_df, reads = _filter_case()
+        dc = DeviceCoverage(cov)
+        assert len(dc) == 7 and dc.keys() == list(cov.keys()) and dc.p == 3
+        got, g_df, r_df = dc.filter(genes_df, reads, minimax, rate)
+        want_cov, want_genes, want_reads = filter_genes(cov, genes_df, reads, minimax, rate)
+        assert got.keys() == list(want_cov.keys())
+        assert g_df.equals(want_genes) and r_df.equals(want_reads)
+        back = got.to_dict()
+        for g in want_cov:
+            np.testing.assert_array_equal(back[g], want_cov[g])
+        assert got.offsets[-1] == sum(m.shape[1] for m in want_cov.values())
+    cov, genes_df, reads = _filter_case()
+    dc = DeviceCoverage(cov)
+    assert dc.select(np.ones(7, dtype=bool)) is dc
+    with pytest.raises(ValueError, match="No genes available"):
+        dc.filter(genes_df, reads, minimax_coverage=10 ** 6)
+    with pytest.raises(ValueError, match="in order"):
+        dc.filter(genes_df.iloc[::-1].reset_index(drop=True), reads)
