@@ -140,3 +140,22 @@ def test_merge_equals_the_unmodified_reference(tmp_path):
         assert list(r2.keys()) == list(g2.keys())
         for g in r2:
             np.testing.assert_array_equal(g2[g], r2[g])
+
+
+def test_merge_in_several_position_groups(tmp_path, monkeypatch):
+    """The chromosome vectors are densified one gene group at a time (coverage_merge._SPAN positions): a span small
+    enough to force a group per gene or two gives the same matrices."""
+    from degnorm_b200 import coverage_merge as cm
+    data_dir, samples, exon, dense = _make_dataset(tmp_path, seed=3)
+    monkeypatch.setattr(cm, "_SPAN", 400)
+    got = cm.merge_chrom_coverage(data_dir, samples, exon[exon.chr == "chr1"], verbose=False)
+    want = _brute_force(samples, exon, dense, "chr1")
+    assert list(got.keys()) == list(want.keys())
+    for g in want:
+        np.testing.assert_array_equal(got[g], want[g])
+    # a gene that runs past the end of the stored chromosome vector is an IndexError, as in the reference
+    bad = exon[exon.chr == "chr2"].copy()
+    bad.loc[bad.gene == "G", "end"] = 10 ** 6
+    bad["gene_end"] = bad.groupby("gene").end.transform("max")
+    with pytest.raises(IndexError):
+        cm.merge_chrom_coverage(data_dir, samples, bad, verbose=False)
