@@ -425,7 +425,6 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
 // inv_lam: 1 / lambda_1 from the last checked step; hint: steps the previous solve needed.
 template <int P, int NW>
 __device__ __forceinline__ int eig_small_core(const KArgs &a, SGene &g, double (&v)[P], bool cold, double &inv_lam, int &hint) {
-    constexpr int NT = NW * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *vx = g.vx + warp * (2 * P);
     const int row = lane % P;
@@ -650,7 +649,7 @@ template <int P, int NW, bool RES, bool CLU>
 __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_small_kernel(const KArgs a) {
     extern __shared__ double smem[];
     using Cfg = SmallCfg<P>;
-    constexpr int NT = NW * 32, CS = P + 2, TC = Cfg::TC;
+    constexpr int NT = NW * 32, TC = Cfg::TC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p;
     const SmallCarve cv = small_carve(P, NW, RES ? a.resident_cols : 0, CLU);
