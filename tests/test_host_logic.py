@@ -286,3 +286,34 @@ def test_device_coverage_handle_filters_like_filter_genes_on_host_tensors():
         dc.filter(genes_df, reads, minimax_coverage=10 ** 6)
     with pytest.raises(ValueError, match="in order"):
         dc.filter(genes_df.iloc[::-1].reset_index(drop=True), reads)
+
+
+def test_mid_kernel_plans_are_pure_host_arithmetic():
+    """dn_make_plan for 13..48 samples (no device call): the 8-warp instantiation takes one CTA per SM with a
+    3 x 51.2 KB ring, the 4-warp one fits two CTAs per SM (G parked in the free ring stage); workspace columns are
+    whole chunks; clusters divide the CTA count."""
+    import ctypes as C
+    from degnorm_b200 import _lib
+    from degnorm_b200.engine import Params
+    lib = _lib.lib()
+    prm = Params().to_c(48)
+    sm, smem = 148, 232448
+
+    def plan(max_cols, n_work, warps, cluster):
+        pl = _lib.DnPlan()
+        rc = lib.dn_make_plan(C.byref(prm), max_cols, n_work, 0, 0, warps, cluster, sm, smem, C.byref(pl))
+        assert rc == 0, lib.dn_last_error()
+        return pl
+    p8 = plan(5000, 10000, 0, 1)
+    assert (p8.tile, p8.threads, p8.cluster, p8.ctas) == (6, 256, 1, 148)
+    assert p8.smem_bytes <= smem and 2 * (p8.smem_bytes + 1024) > smem          # one CTA per SM
+    assert p8.ws_cols == 5056 and p8.ws_cols % 64 == 0
+    p4 = plan(5000, 10000, 4, 1)
+    assert (p4.tile, p4.threads, p4.ctas) == (6, 128, 296)
+    assert 2 * (p4.smem_bytes + 1024) <= smem + 1024                             # two CTAs per SM
+    assert p4.ws_cols == 5024 and p4.ws_cols % 32 == 0
+    pc = plan(40000, 5, 0, 4)
+    assert (pc.cluster, pc.ctas, pc.ws_cols) == (4, 20, 10048)
+    assert plan(40000, 1000, 0, 16).ctas == 144                                   # 9 clusters of 16 on 148 SMs
+    pl = _lib.DnPlan()
+    assert lib.dn_make_plan(C.byref(prm), 5000, 10, 0, 0, 0, 3, sm, smem, C.byref(pl)) != 0      # cluster of 3
