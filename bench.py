@@ -334,7 +334,8 @@ def main():
             traffic, traffic_src = float(tj["dram_bytes_per_launch_group"]), "profiles/r01_traffic_%s.json (ncu)" % args.config
     except Exception:
         pass
-    roofline = dict(bound="hbm", kernel="nmfoa_kernel (fused baseline selection; one launch group per outer iteration)",
+    kname = "nmfoa_small_kernel" if p <= 12 else ("nmfoa_mid_kernel" if p <= 48 else "nmfoa_kernel (tiled)")
+    roofline = dict(bound="hbm", kernel=kname + " (fused baseline selection; one launch group per outer iteration)",
                     achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                     traffic_source=traffic_src,
                     peak_source="MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
