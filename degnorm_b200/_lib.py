@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # DEGNORM_B200_LIB: tuning aid, another build of the same library (build.py variants); still no fallback
 LIB_PATH = os.environ.get("DEGNORM_B200_LIB") or os.path.join(HERE, "libdegnorm_b200.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 DN_NCOUNTERS = 8
 DN_MAX_BINS = 64
 DN_MAX_SAMPLES = 256
@@ -15,13 +15,16 @@ CNT_EXIT, CNT_N_HICOV, CNT_NMF_CALLS, CNT_SUM_COLS, CNT_EIG_STEPS, CNT_DROPS_LO,
 EXIT_NAMES = {0: "none", 1: "few_hicov", 2: "empty_sample", 3: "median", 4: "no_selection", 5: "refined",
               6: "fallback_high", 7: "fallback", -1: "plan_error"}
 
+DN_FLAG_PLAIN_NMF, DN_FLAG_RAW_RHO = 1, 2
+(DN_EXIT_NONE, DN_EXIT_FEW_HICOV, DN_EXIT_EMPTY_SAMPLE, DN_EXIT_MEDIAN, DN_EXIT_NO_SELECTION, DN_EXIT_REFINED,
+ DN_EXIT_FALLBACK_HIGH, DN_EXIT_FALLBACK) = range(8)
 DN_ERR_INVALID, DN_ERR_CUDA, DN_ERR_UNSUPPORTED, DN_ERR_WORKSPACE = -1, -2, -3, -4
 
 
 class DnParams(C.Structure):
     _fields_ = [("p", C.c_int32), ("nmf_iter", C.c_int32), ("bins", C.c_int32), ("min_bins", C.c_int32),
                 ("min_high_coverage", C.c_int32), ("downsample_rate", C.c_int32), ("min_gene_len", C.c_int32),
-                ("skip_baseline_selection", C.c_int32)]
+                ("skip_baseline_selection", C.c_int32), ("flags", C.c_int32)]
 
 
 class DnPlan(C.Structure):

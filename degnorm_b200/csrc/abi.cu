@@ -206,6 +206,7 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
     a.bins = prm->bins; a.min_bins = prm->min_bins; a.min_hi = prm->min_high_coverage;
     a.rate = mode == MODE_INIT ? 1 : prm->downsample_rate; a.skip = prm->skip_baseline_selection;
     a.min_len = prm->min_gene_len;
+    a.flags = mode == MODE_INIT ? 0 : prm->flags;
     a.rho = rho; a.ran = ran; a.counters = counters; a.kfac = kfac; a.e_first = e_first;
     a.est_rowsum = est_rowsum; a.cov_rowsum = cov_rowsum;
     a.row_max = row_max; a.row_max_out = row_max_out;

@@ -38,6 +38,7 @@ struct KArgs {
     int nmf_iter;
     double c;
     int bins, min_bins, min_hi, rate, skip, min_len;
+    int flags;              // DN_FLAG_* (single-matrix helper methods)
     double *rho;
     unsigned char *ran;
     int *counters;

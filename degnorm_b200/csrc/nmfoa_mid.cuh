@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
             }
         }
         const double gmax = block_max<MNT>(tmax, g.red);
-        const double thr = 0.1 * gmax;                                   // nmf.py:76
+        const double thr = (a.flags & DN_FLAG_PLAIN_NMF) ? -1.0e300 : 0.1 * gmax;                                   // nmf.py:76
         const int rate = a.rate;
         const int start = (rate > 1 && a.ds_start) ? a.ds_start[gid] : 0;
         const int ncand = start < L ? (L - start + rate - 1) / rate : 0;
@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
             }
             bool any_empty = false;
             for (int i = 0; i < p; ++i) any_empty |= !(g.rs0[i] > 0.0);
-            if (any_empty) {
+            if (any_empty && !(a.flags & DN_FLAG_PLAIN_NMF)) {
                 exit_code = DN_EXIT_EMPTY_SAMPLE;
             } else {
                 const bool store_e = (a.e_first != nullptr) && (n0 == L);
@@ -776,7 +776,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
                             g.rsC0[tid] = g.rsC[tid];
                         }
                         __syncthreads();
-                        if (median_one_minus(g.rho, p) > 1.0) { exit_code = DN_EXIT_MEDIAN; break; }
+                        if (!(a.flags & DN_FLAG_PLAIN_NMF) && median_one_minus(g.rho, p) > 1.0) { exit_code = DN_EXIT_MEDIAN; break; }
                         double rmin = g.rho[0];
                         rmax = g.rho[0];
                         for (int i = 1; i < p; ++i) { rmin = fmin(rmin, g.rho[i]); rmax = fmax(rmax, g.rho[i]); }
@@ -901,8 +901,8 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
         if (g.crank == 0) {
             if (tid < p) {
                 double r = is_default ? 0.0 : g.rho[tid];
-                r = r > 0.9 ? 0.9 : r;
-                r = r < 0.0 ? 0.0 : r;
+                if (!(a.flags & DN_FLAG_RAW_RHO)) r = r > 0.9 ? 0.9 : r;
+                if (!(a.flags & DN_FLAG_RAW_RHO)) r = r < 0.0 ? 0.0 : r;
                 a.rho[(long long)gid * p + tid] = r;
                 if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
             }

@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
             }
         }
         const double gmax = block_max<NT>(tmax, g.red);
-        const double thr = 0.1 * gmax;                                   // nmf.py:76
+        const double thr = (a.flags & DN_FLAG_PLAIN_NMF) ? -1.0e300 : 0.1 * gmax;                                   // nmf.py:76
         // (2) keep the columns that are high coverage (strict >) and on the systematic sample (nmf.py:220-229),
         //     scaled, compacted in order into the working buffer.  In a cluster every CTA takes a contiguous
         //     share of the candidates.
@@ -846,7 +846,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
             }
             bool any_empty = false;
             for (int i = 0; i < p; ++i) any_empty |= !(g.rs0[i] > 0.0);
-            if (any_empty) {
+            if (any_empty && !(a.flags & DN_FLAG_PLAIN_NMF)) {
                 exit_code = DN_EXIT_EMPTY_SAMPLE;                        // nmf.py:241-242
             } else {
                 const bool store_e = (a.e_first != nullptr) && (n0 == L);
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
                             g.rsC0[tid] = g.rsC[tid];
                         }
                         bsync<NW>();
-                        if (median_one_minus(g.rho, p) > 1.0) {
+                        if (!(a.flags & DN_FLAG_PLAIN_NMF) && median_one_minus(g.rho, p) > 1.0) {
                             exit_code = DN_EXIT_MEDIAN;                  // nmf.py:257-258
                             break;
                         }
@@ -1007,8 +1007,8 @@ __global__ void __launch_bounds__(NW * 32, (12 / NW) > 0 ? (12 / NW) : 1) nmfoa_
         if (g.crank == 0) {
             if (tid < p) {
                 double r = is_default ? 0.0 : g.rho[tid];
-                r = r > 0.9 ? 0.9 : r;                                   // nmf.py:398-399
-                r = r < 0.0 ? 0.0 : r;
+                if (!(a.flags & DN_FLAG_RAW_RHO)) r = r > 0.9 ? 0.9 : r;                                   // nmf.py:398-399
+                if (!(a.flags & DN_FLAG_RAW_RHO)) r = r < 0.0 ? 0.0 : r;
                 a.rho[(long long)gid * p + tid] = r;
                 if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
             }

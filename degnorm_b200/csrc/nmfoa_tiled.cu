@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(NT, TR == 4 ? 2 : 1) nmfoa_kernel(const KArgs 
             }
         }
         const double gmax = block_max<NT>(tmax, g.red);
-        const double thr = 0.1 * gmax;                                   // nmf.py:76
+        const double thr = (a.flags & DN_FLAG_PLAIN_NMF) ? -1.0e300 : 0.1 * gmax;                                   // nmf.py:76
         // (2) count the kept columns: high coverage (strict >) and on the systematic sample (nmf.py:220-229)
         const int rate = a.rate;
         const int start = (rate > 1 && a.ds_start) ? a.ds_start[gid] : 0;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(NT, TR == 4 ? 2 : 1) nmfoa_kernel(const KArgs 
             __syncthreads();
             bool any_empty = false;
             for (int i = 0; i < p; ++i) any_empty |= !(g.rs0[i] > 0.0);
-            if (any_empty) {
+            if (any_empty && !(a.flags & DN_FLAG_PLAIN_NMF)) {
                 exit_code = DN_EXIT_EMPTY_SAMPLE;                        // nmf.py:241-242
             } else {
                 const bool store_e = (a.e_first != nullptr) && (n0 == L);
@@ -694,7 +694,7 @@ __global__ void __launch_bounds__(NT, TR == 4 ? 2 : 1) nmfoa_kernel(const KArgs 
                     g.rsC0[tid] = g.rsC[tid];
                 }
                 __syncthreads();
-                if (median_one_minus(g.rho, p) > 1.0) {
+                if (!(a.flags & DN_FLAG_PLAIN_NMF) && median_one_minus(g.rho, p) > 1.0) {
                     exit_code = DN_EXIT_MEDIAN;                          // nmf.py:257-258
                 } else {
                     double rmin = g.rho[0], rmax = g.rho[0];
@@ -795,8 +795,8 @@ __global__ void __launch_bounds__(NT, TR == 4 ? 2 : 1) nmfoa_kernel(const KArgs 
         }
         if (tid < p) {
             double r = is_default ? 0.0 : g.rho[tid];
-            r = r > 0.9 ? 0.9 : r;                                       // nmf.py:398-399
-            r = r < 0.0 ? 0.0 : r;
+            if (!(a.flags & DN_FLAG_RAW_RHO)) r = r > 0.9 ? 0.9 : r;                                       // nmf.py:398-399
+            if (!(a.flags & DN_FLAG_RAW_RHO)) r = r < 0.0 ? 0.0 : r;
             a.rho[(long long)gid * p + tid] = r;
             if (a.kfac) a.kfac[(long long)gid * p + tid] = is_default ? 0.0 : g.K[tid];
         }

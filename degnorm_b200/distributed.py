@@ -101,12 +101,17 @@ class TorchComm(object):
             self.dist.all_reduce(t, group=self.group)
         return t
 
+    def _global(self, r):
+        # send/recv_object_list address GLOBAL ranks; callers of this class speak group ranks
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
     def send_obj(self, obj, dest, tag=0):
-        self.dist.send_object_list([obj], dst=dest, group=self.group)
+        # (torch has no message tags for objects: messages between a pair of ranks are matched in order)
+        self.dist.send_object_list([obj], dst=self._global(dest), group=self.group)
 
     def recv_obj(self, source, tag=0):
         box = [None]
-        self.dist.recv_object_list(box, src=source, group=self.group)
+        self.dist.recv_object_list(box, src=self._global(source), group=self.group)
         return box[0]
 
     def barrier(self):

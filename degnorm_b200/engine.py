@@ -43,11 +43,11 @@ class Params(object):
         if self.downsample_rate < 1:
             raise ValueError("downsample_rate must be >= 1")
 
-    def to_c(self, p):
+    def to_c(self, p, flags=0):
         # nmf.py:261 evaluates max(2, ceil(200.0 * (1 / rate))) in floating point; do the same
         min_len = int(max(2, np.ceil(200.0 * (1 / self.downsample_rate))))
         return DnParams(int(p), self.nmf_iter, self.bins, self.min_bins, self.min_high_coverage,
-                        self.downsample_rate, min_len, int(self.skip_baseline_selection))
+                        self.downsample_rate, min_len, int(self.skip_baseline_selection), int(flags))
 
 
 def draw_offsets(n_genes, prm):
@@ -266,6 +266,17 @@ class ShardEngine(object):
             torch.distributed.all_reduce(t, group=self.group)
 
     def run(self, ds_offsets=None, want_estimates=True, est_host=None, keep_for_estimates=False):
+        """See _run; the engine's device is made current for the duration of the call (the library launches on the
+        current device)."""
+        with torch.cuda.device(self.device):
+            return self._run(ds_offsets, want_estimates, est_host, keep_for_estimates)
+
+    def estimates(self, gene_ids):
+        """See _estimates; runs with the engine's device current."""
+        with torch.cuda.device(self.device):
+            return self._estimates(gene_ids)
+
+    def _run(self, ds_offsets=None, want_estimates=True, est_host=None, keep_for_estimates=False):
         """ds_offsets: int32 numpy [degnorm_iter, n] (this shard's genes) or None.  Results -> self.out.
         est_host: pinned float64 host tensor of p * sum(L) elements: the estimates are then laid out in WORK order
         (bucket by bucket, self.est_off) and each bucket's block is copied to the host as soon as the bucket has
@@ -323,6 +334,9 @@ class ShardEngine(object):
                                 C.c_void_p(main.cuda_stream)))
         self.launches += 1
         scale_used = scale.clone()
+        # scale factors after the init pass and after every outer iteration (the reference logs them, nmf.py:537, 592)
+        scale_hist = torch.zeros((n_iter + 1, p), **f64)
+        scale_hist[0].copy_(scale)
 
         # ---- outer DegNorm iterations (nmf.py:560-596)
         for it in range(n_iter):
@@ -370,6 +384,7 @@ class ShardEngine(object):
             check(lib.dn_outer_apply(_ptr(sums), nn if n == 0 else n, p, _ptr(x_w), _ptr(rho), _ptr(x_adj), _ptr(norm),
                                      _ptr(scale), C.c_void_p(main.cuda_stream)))
             self.launches += 1
+            scale_hist[it + 1].copy_(scale)
 
         if want_estimates and n > 0 and n_iter > 0 and not overlap_est:
             b = self.init_bucket
@@ -380,12 +395,13 @@ class ShardEngine(object):
         mark("end")
         self.out = dict(rho=rho[:n], rho0=rho0[:n], x_adj=x_adj[:n], x_weighted=x_w[:n], norm_factors=norm,
                         scale_factors=scale, ran=ran[:, :n], counters=counters[:, :n], init_counters=init_counters[:n],
-                        est=est, kfac=kfac[:n], scale_used=scale_used, est_in_work_order=overlap_est)
+                        est=est, kfac=kfac[:n], scale_used=scale_used, est_in_work_order=overlap_est,
+                        scale_hist=scale_hist)
         self._e_first = e_first
         self._can_estimate = (want_estimates or keep_for_estimates) and n > 0 and n_iter > 0
         return self.out
 
-    def estimates(self, gene_ids):
+    def _estimates(self, gene_ids):
         """Full-length estimates (nmf.py:217, 247, 333-365) of the listed genes of the last run(), materialised on
         demand: one dn_estimates launch over just those genes into a compact buffer.  Returns (device tensor,
         column offsets [len(ids) + 1]); gene k's block is est[p * o[k] : p * o[k + 1]] viewed as p x L."""
@@ -411,6 +427,59 @@ class ShardEngine(object):
                                     _ptr(self._e_first), _ptr(est_off_dev), _ptr(est), C.c_void_p(main.cuda_stream)))
         self.launches += 1
         return est, sub
+
+    def check_exit_codes(self, counters_host=None):
+        """A negative exit code means a gene did not fit the plan of the bucket it was put in (planner or ABI misuse):
+        its row then holds the default result, which would silently distort the normalisation -- refuse instead."""
+        cnt = counters_host if counters_host is not None else self.out["counters"].cpu().numpy()
+        bad = np.argwhere(cnt[..., _lib.CNT_EXIT] < 0)
+        if len(bad):
+            raise _lib.DegnormCudaError("%d gene-iterations did not fit their launch plan (first: iteration %d, gene %d)"
+                                        % (len(bad), int(bad[0][0]), int(bad[0][-1])))
+
+    # ---------------------------------------------------------------------------------------------------------
+    def fit_once(self, scale=None, ds_row=None, flags=0, want_estimates=False, clamp_estimates=False):
+        """ONE pass of the fused kernel over this shard's genes outside the run() flow: what the single-matrix
+        methods of the class need (GeneNMFOA.nmf / rank_one_approx / ratio_svd / baseline_selection,
+        nmf.py:55-121, 189-372).  scale: p doubles (default ones: the matrices are taken as they are); flags:
+        _lib.DN_FLAG_*.  Returns device tensors rho (n x p), ran (n), counters, kfac = K (n x p), e_first = E of the
+        first fit (packed like the coverage, one row per gene) and, on request, the full-length estimates;
+        clamp_estimates asks for max(K.E, x) (ratio_svd, nmf.py:118-119) where the fit was kept unclamped."""
+        with torch.cuda.device(self.device):
+            p, n, dev, lib = self.p, self.n, self.device, self.lib
+            f64 = dict(dtype=torch.float64, device=dev)
+            cprm = self.prm.to_c(p, flags)
+            main = torch.cuda.current_stream(dev)
+            scale_t = torch.ones(p, **f64) if scale is None else torch.as_tensor(scale, **f64).contiguous()
+            rho = torch.zeros((n, p), **f64)
+            kfac = torch.zeros((n, p), **f64)
+            ran = torch.zeros(n, dtype=torch.uint8, device=dev)
+            counters = torch.zeros((n, _lib.DN_NCOUNTERS), dtype=torch.int32, device=dev)
+            e_first = torch.zeros(int(self.offsets_np[-1]), **f64) if self.prm.downsample_rate == 1 else None
+            ds_dev = (torch.from_numpy(np.ascontiguousarray(ds_row, dtype=np.int32)).to(dev)
+                      if ds_row is not None else None)
+            # the matrix maximum behind the high-coverage threshold (nmf.py:76) is found by the kernel itself here
+            for b in self.buckets:
+                check(lib.dn_baseline_selection(
+                    _ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(cprm), C.byref(b.plan),
+                    _ptr(scale_t), _ptr(ds_dev), C.c_void_p(0), _ptr(rho), _ptr(ran), _ptr(counters), _ptr(kfac),
+                    _ptr(e_first), C.c_void_p(0), C.c_void_p(0), _ptr(b.ws), b.ws.numel(),
+                    C.c_void_p(main.cuda_stream)))
+                self.launches += 1
+            est = None
+            if want_estimates:
+                cnt = counters
+                if clamp_estimates:
+                    cnt = counters.clone()
+                    kept = cnt[:, _lib.CNT_EXIT] == _lib.DN_EXIT_NO_SELECTION
+                    cnt[kept, _lib.CNT_EXIT] = _lib.DN_EXIT_FALLBACK      # same K, E; estimate = max(K.E, x)
+                est = torch.empty_like(self.cov)
+                b = self.init_bucket
+                check(lib.dn_estimates(_ptr(self.cov), _ptr(self.off_dev), _ptr(b.order), b.n, C.byref(cprm),
+                                       _ptr(scale_t), _ptr(cnt), _ptr(kfac), _ptr(e_first), C.c_void_p(0), _ptr(est),
+                                       C.c_void_p(main.cuda_stream)))
+                self.launches += 1
+            return dict(rho=rho, ran=ran, counters=counters, kfac=kfac, e_first=e_first, est=est)
 
     # ---------------------------------------------------------------------------------------------------------
     def phase_ms(self):

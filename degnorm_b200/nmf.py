@@ -22,6 +22,7 @@ import warnings
 import numpy as np
 import torch
 
+from . import _lib
 from .engine import Params, ShardEngine, draw_offsets
 from .packing import pack_coverage, pinned_buffer, unpack_estimates
 
@@ -70,6 +71,34 @@ class LazyEstimates(object):
             lo = hi
 
 
+def _single_matrix_engine(x, device, **kw):
+    """A one-gene ShardEngine around x (p x L): the device path behind the single-matrix methods."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("degnorm_b200 needs a CUDA device (B200); there is no CPU fallback")
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim != 2 or min(x.shape) < 2:
+        # scipy's svds(k=1) refuses such input (nmf.py:63); the reference swallows this ValueError in its drop loop
+        raise ValueError("`k` must be an integer satisfying `0 < k < min(A.shape)`.")
+    dev = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+    p, L = x.shape
+    with torch.cuda.device(dev):
+        flat = torch.from_numpy(np.ascontiguousarray(x).ravel()).to(dev)
+        eng = ShardEngine(Params(**kw), p, dev)
+        eng.load(flat, np.array([0, L], dtype=np.int64), torch.ones((1, p), dtype=torch.float64, device=dev))
+    return eng, x
+
+
+def _factorise(x, nmf_iter, device):
+    """K (p x 1), E (1 x L) of nmf() (nmf.py:78-107) -- of rank_one_approx (nmf.py:55-64) when nmf_iter = 0 -- on
+    the matrix as it is, through the fused kernel (DN_FLAG_PLAIN_NMF).  Sign convention: K >= 0, E >= 0."""
+    eng, x = _single_matrix_engine(x, device, degnorm_iter=1, nmf_iter=nmf_iter, min_high_coverage=2,
+                                   skip_baseline_selection=True)
+    out = eng.fit_once(flags=_lib.DN_FLAG_PLAIN_NMF)
+    K = out["kfac"].cpu().numpy().reshape(-1, 1)
+    E = out["e_first"].cpu().numpy().reshape(1, -1)
+    return K, E, eng, out
+
+
 class GeneNMFOA(object):
 
     def __init__(self, degnorm_iter=5, downsample_rate=1, min_high_coverage=50, nmf_iter=100, bins=20, n_jobs=1,
@@ -106,6 +135,47 @@ class GeneNMFOA(object):
         self.timings = {}
         self._host_cache = {}      # pinned staging buffers, re-used by later run() calls on this object
         self._group = None         # torch.distributed group: this object's genes are one shard of a larger run
+
+    # ---- single-matrix methods of the reference (public by convention), on the device path -----------------------
+    @staticmethod
+    def rank_one_approx(x, device=None):
+        """nmf.py:55-64: (K, E) = (u * s, vh) of the top singular triplet of x; here from the p x p Gram
+        eigenvector, with K >= 0 and E >= 0 (the reference's signs are arbitrary, only K.dot(E) and |K| are used)."""
+        K, E, _, _ = _factorise(x, 0, device)
+        return K, E
+
+    def nmf(self, x, factors=False):
+        """nmf.py:78-107: NMF-OA of x (no final clamp, as in the reference); (K, E) if factors else K.dot(E)."""
+        K, E, _, _ = _factorise(x, self.nmf_iter, self.device)
+        return (K, E) if factors else K.dot(E)
+
+    def ratio_svd(self, x):
+        """nmf.py:109-121: rank-one product clamped from below by x."""
+        _, _, eng, _ = _factorise(x, 0, self.device)
+        out = eng.fit_once(flags=_lib.DN_FLAG_PLAIN_NMF, want_estimates=True, clamp_estimates=True)
+        return out["est"].cpu().numpy().reshape(np.shape(x))
+
+    def run_ratio_svd_serial(self, x):
+        """nmf.py:123-124"""
+        return list(map(self.ratio_svd, x))
+
+    def baseline_selection(self, F):
+        """nmf.py:189-372 for ONE gene (F is taken as it is, i.e. already scaled): (rho, estimate, ran) with rho as
+        the reference returns it (unclipped).  self.p must be set (run() sets it; the reference needs it too).
+        With down-sampling the start offset is drawn from the global numpy stream like nmf.py:420-422."""
+        F = np.asarray(F, dtype=np.float64)
+        ds = None
+        if self.downsample_rate > 1:
+            if self.downsample_rate >= F.shape[1]:
+                raise ValueError('Cannot downsample at a rate < 1 / length(gene)')
+            ds = np.array([np.random.choice(self.downsample_rate)], dtype=np.int32)
+        eng, F = _single_matrix_engine(F, self.device, degnorm_iter=1, nmf_iter=self.nmf_iter, bins=self.bins,
+                                       downsample_rate=self.downsample_rate, min_high_coverage=self.min_high_coverage,
+                                       skip_baseline_selection=self.skip_baseline_selection)
+        out = eng.fit_once(ds_row=ds, flags=_lib.DN_FLAG_RAW_RHO, want_estimates=True)
+        if int(out["counters"][0, _lib.CNT_EXIT]) < 0:
+            raise _lib.DegnormCudaError("gene does not fit the launch plan")
+        return (out["rho"].cpu().numpy()[0], out["est"].cpu().numpy().reshape(F.shape), bool(out["ran"][0].item()))
 
     # ---- small host helpers the reference exposes as (static) methods -------------------------------------------
     @staticmethod
@@ -226,6 +296,8 @@ class GeneNMFOA(object):
             self.scale_factors = out["scale_factors"].cpu().numpy()
             self.ran_baseline_selection = out["ran"].cpu().numpy().T.astype(bool)
             self.counters = out["counters"].cpu().numpy()
+            eng.check_exit_codes(self.counters)
+            self._log_run(out["scale_hist"].cpu().numpy())
             estimates = None
             if lazy and self.n_genes > 0 and self.degnorm_iter > 0:
                 estimates = LazyEstimates(eng, gene_lengths)
@@ -243,6 +315,18 @@ class GeneNMFOA(object):
         self.timings = dict(pack_s=t1 - t0, device_s=t2 - t1, unpack_s=t3 - t2, total_s=t3 - t0,
                             launches=eng.launches)
         return estimates
+
+    def _log_run(self, scale_hist):
+        """The reference's logging.info lines (nmf.py:537-538, 571-572, 592-593), same text and order.  The whole
+        run is queued on the device without a host synchronisation, so they are emitted once it has finished."""
+        logging.info('Initial sequencing depth scale factors -- \n\t{0}'
+                     .format(', '.join([str(x) for x in scale_hist[0]])))
+        for i in range(self.degnorm_iter):
+            if not self.skip_baseline_selection:
+                logging.info('DegNorm iteration {0} -- {1} genes sent through baseline selection'
+                             .format(i + 1, np.sum(self.ran_baseline_selection[:, i])))
+            logging.info('DegNorm iteration {0} -- sequencing depth scale factors: \n\t{1}'
+                         .format(i + 1, ', '.join([str(x) for x in scale_hist[i + 1]])))
 
     # ---- output writer (host side, same files and columns as nmf.py:603-711) --------------------------------------
     def save_results(self, estimates, gene_manifest_df, output_dir='.', sample_ids=None):

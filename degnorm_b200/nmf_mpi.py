@@ -55,23 +55,29 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
                  nmf_iter=nmf_iter, bins=bins, n_jobs=n_jobs, skip_baseline_selection=skip_baseline_selection,
                  random_state=random_state)
     rank, size = c.rank, c.size
+    if partition not in ('balanced', 'contiguous'):          # (checked on every rank: nobody is left waiting)
+        raise ValueError("partition must be 'balanced' or 'contiguous'")
     # one GPU per worker; made current before any communication (NCCL object collectives stage through it)
     dev = torch.device(device if device is not None else "cuda:%d" % (rank % torch.cuda.device_count()))
     torch.cuda.set_device(dev)
     if rank == 0:
-        genes = list(cov_dat.keys())
-        n_genes = len(genes)
-        x = np.ascontiguousarray(np.copy(reads_dat), dtype=np.float64)
-        mats = list(cov_dat.values())
-        p = _check_input(x, mats, n_genes, prm)
-        ds = draw_offsets(n_genes, prm)                     # seeds the global numpy stream (nmf.py:556)
-        if partition == 'contiguous':
-            shards = [np.arange(lo, hi) for lo, hi in partition_bounds(n_genes, size)]
-        elif partition == 'balanced':
-            li = np.array([m.shape[1] for m in mats], dtype=np.int64)
-            shards = balanced_partition(p * ((li + prm.downsample_rate - 1) // prm.downsample_rate), size)
-        else:
-            raise ValueError("partition must be 'balanced' or 'contiguous'")
+        try:
+            genes = list(cov_dat.keys())
+            n_genes = len(genes)
+            x = np.ascontiguousarray(np.copy(reads_dat), dtype=np.float64)
+            mats = list(cov_dat.values())
+            p = _check_input(x, mats, n_genes, prm)
+            ds = draw_offsets(n_genes, prm)                     # seeds the global numpy stream (nmf.py:556)
+            if partition == 'contiguous':
+                shards = [np.arange(lo, hi) for lo, hi in partition_bounds(n_genes, size)]
+            else:
+                li = np.array([m.shape[1] for m in mats], dtype=np.int64)
+                shards = balanced_partition(p * ((li + prm.downsample_rate - 1) // prm.downsample_rate), size)
+        except Exception as exc:
+            # the workers are waiting for their shard: tell them, so that every rank raises instead of hanging
+            for w in range(1, size):
+                c.send_obj(dict(error="%s: %s" % (type(exc).__name__, exc)), dest=w, tag=333 + w)
+            raise
 
         def shard(idx):
             return dict(p=p, mats=[mats[g] for g in idx], reads=x[idx], ds=None if ds is None else ds[:, idx])
@@ -83,6 +89,8 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
         mine = shard(shards[0])
     else:
         mine = c.recv_obj(source=0, tag=333 + rank)
+        if "error" in mine:
+            raise ValueError("rank 0 rejected the input -- " + mine["error"])
     p = mine["p"]
     with torch.cuda.device(dev):
         flat, offsets = pack_coverage(mine["mats"], p) if len(mine["mats"]) else (torch.zeros(0, dtype=torch.float64),
@@ -92,6 +100,7 @@ def run_gene_nmfoa_mpi(comm, cov_dat, reads_dat, degnorm_iter=5, downsample_rate
                                                           .reshape(-1, p)).to(dev))
         out = eng.run(mine["ds"], want_estimates=return_estimates)
         torch.cuda.synchronize(dev)
+        eng.check_exit_codes()
         part = dict(rho=out["rho"].cpu().numpy(), x_adj=out["x_adj"].cpu().numpy(),
                     ran=out["ran"].cpu().numpy().T.astype(bool), est=None)
         if return_estimates and out["est"] is not None:

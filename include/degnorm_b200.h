@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DN_ABI_VERSION 5
+#define DN_ABI_VERSION 6
 #define DN_MAX_BINS 64      /* baseline-selection bins held in the fused kernel (reference default: 20) */
 #define DN_MAX_SAMPLES 256  /* p supported by the fused kernels (one thread per sample in the n x p steps) */
 #define DN_NCOUNTERS 8      /* int32 counters per gene, see dn_counter */
@@ -76,7 +76,17 @@ typedef struct dn_params {
     int32_t downsample_rate;    /* -d, systematic "take every" rate (nmf.py:36)                   */
     int32_t min_gene_len;       /* max(2, ceil(200*(1/rate))) evaluated as the reference does (nmf.py:261) */
     int32_t skip_baseline_selection; /* -s (nmf.py:265)                                          */
+    int32_t flags;              /* 0 for GeneNMFOA.run; DN_FLAG_* for the single-matrix helper methods            */
 } dn_params;
+
+/* dn_params.flags: what the single-matrix methods of the class need from dn_baseline_selection.
+ * DN_FLAG_PLAIN_NMF: the matrix is factorised as it is -- GeneNMFOA.nmf / rank_one_approx / ratio_svd
+ *   (nmf.py:55-121): no high-coverage filter, no early exits (nmf.py:232-258), one nmf() call (set skip too);
+ *   kfac receives K = u*s (>= 0 by convention), e_first receives E = vh.
+ * DN_FLAG_RAW_RHO: rho is written as baseline_selection returns it (nmf.py:372), without the [0, 0.9] clip that
+ *   par_apply_baseline_selection applies afterwards (nmf.py:398-399). */
+#define DN_FLAG_PLAIN_NMF 1
+#define DN_FLAG_RAW_RHO 2
 
 /* Launch plan for one bucket of genes (all genes of one launch share a shared-memory carve-up). */
 typedef struct dn_plan {

@@ -103,6 +103,41 @@ def save_case(name, cov_mats, reads, kwargs, **kw):
                                                          os.path.getsize(path) / 1024.0))
 
 
+def input_digest(cov_mats, reads):
+    import hashlib
+    h = hashlib.sha256()
+    for m in cov_mats:
+        h.update(np.ascontiguousarray(m).tobytes())
+    h.update(np.ascontiguousarray(reads).tobytes())
+    return h.hexdigest()
+
+
+def save_seeded_case(name, synth_kw, kwargs, **kw):
+    """Large cases (p = 17 ... 200, genes of tens of thousands of columns): the fixture keeps the generator
+    arguments, a digest of the generated inputs and the reference's n x p outputs (plus the row sums of its
+    estimates); tests regenerate the inputs with synth_numpy (tests/conftest.py:load_seeded_case checks the digest)."""
+    lengths = np.asarray(synth_kw["lengths"], dtype=np.int64)
+    cov_mats, reads = synth_numpy(len(lengths), synth_kw["p"], synth_kw["seed"], lengths=lengths,
+                                  fortran_every=synth_kw.get("fortran_every", 0), jitter=synth_kw.get("jitter", 0.0))
+    out = run_reference(cov_mats, reads, kwargs, **kw)
+    p = cov_mats[0].shape[0]
+    ests, pos = [], 0
+    for L in lengths:
+        ests.append(out["est_flat"][pos:pos + p * int(L)].reshape(p, int(L)))
+        pos += p * int(L)
+    out["est_rowsum"] = np.array([e.sum(axis=1) for e in ests])
+    out["est_max"] = np.array([e.max(axis=1) for e in ests])
+    del out["est_flat"]
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, lengths=lengths, p=np.int64(p), seed=np.int64(synth_kw["seed"]),
+                        fortran_every=np.int64(synth_kw.get("fortran_every", 0)),
+                        jitter=np.float64(synth_kw.get("jitter", 0.0)), digest=np.array(input_digest(cov_mats, reads)),
+                        kw_keys=np.array(list(kwargs.keys())), kw_vals=np.array([float(v) for v in kwargs.values()]),
+                        **out)
+    print("%-14s %3d genes  ref %.1fs  -> %s (%.0f KB)" % (name, len(cov_mats), out["ref_seconds"], path,
+                                                         os.path.getsize(path) / 1024.0))
+
+
 def case_kat():
     """SURVEY.md Appendix B.5 known-answer inputs, through the reference's own nmf() and ratio_svd()."""
     x = np.array([[10, 12, 14, 16, 18, 20, 22, 24], [5, 6, 7, 8, 9, 10, 11, 12], [2, 4, 9, 12, 14, 19, 22, 25]],
@@ -147,6 +182,26 @@ def main(which):
         "run_p3_bins": lambda: save_case(
             "run_p3_bins", *synth_numpy(6, 3, 105, lengths=lengths_uniform(6, 220, 900, 5), jitter=J),
             dict(degnorm_iter=2, nmf_iter=40, bins=10, min_high_coverage=30)),
+        # ---- seeded cases at the reference's real settings (nmf_iter = 100, >= 2 outer iterations) for the kernels
+        # of 13..48 samples (mid-p), > 48 samples, and the long-gene tiers (clusters, streamed slabs)
+        "seed_p17": lambda: save_seeded_case(
+            "seed_p17", dict(p=17, seed=201, lengths=lengths_uniform(6, 300, 2500, 11), jitter=J, fortran_every=3),
+            dict(degnorm_iter=2, nmf_iter=100)),
+        "seed_p48": lambda: save_seeded_case(
+            "seed_p48", dict(p=48, seed=202, lengths=lengths_uniform(6, 300, 3000, 12), jitter=J, fortran_every=2),
+            dict(degnorm_iter=3, nmf_iter=100)),
+        "seed_p48_long": lambda: save_seeded_case(
+            "seed_p48_long", dict(p=48, seed=203, lengths=np.array([20000, 40000, 900]), jitter=J),
+            dict(degnorm_iter=2, nmf_iter=100)),
+        "seed_p200": lambda: save_seeded_case(
+            "seed_p200", dict(p=200, seed=204, lengths=np.array([260, 520, 900, 1500]), jitter=J),
+            dict(degnorm_iter=2, nmf_iter=100)),
+        "seed_p100": lambda: save_seeded_case(
+            "seed_p100", dict(p=100, seed=206, lengths=np.array([300, 700, 1300]), jitter=J),
+            dict(degnorm_iter=2, nmf_iter=100)),
+        "seed_p12_long": lambda: save_seeded_case(
+            "seed_p12_long", dict(p=12, seed=205, lengths=np.array([40000, 160000, 300000, 2000]), jitter=J),
+            dict(degnorm_iter=2, nmf_iter=100)),
     }
     for name in (which or list(cases)):
         cases[name]()

@@ -222,3 +222,20 @@ def test_two_processes_on_one_gpu_equal_single_process(partition):
     np.testing.assert_allclose(out["x_adj"], single.x_adj, rtol=1e-12, atol=1e-12)
     for a, b in zip(out["estimates"], est):
         np.testing.assert_allclose(a, b, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_mpi_twin_over_nccl_one_rank_per_gpu():
+    """run_gene_nmfoa_mpi with a torch.distributed NCCL group, one rank per GPU (torchrun), against the single-GPU
+    class on rank 0 (tools/mpi_twin_nccl.py asserts DI / adjusted counts / estimates / flags).  Needs two devices."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), os.path.join(root, "tools", "mpi_twin_nccl.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "mpi twin over NCCL, 2 ranks" in r.stdout

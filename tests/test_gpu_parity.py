@@ -8,7 +8,7 @@ from collections import OrderedDict
 import numpy as np
 import pytest
 
-from conftest import load_case, RUN_CASES
+from conftest import load_case, load_seeded_case, RUN_CASES, SEEDED_CASES, GOLDEN
 
 pytestmark = pytest.mark.gpu
 
@@ -50,6 +50,109 @@ def test_golden_reference_cases(case):
     np.testing.assert_array_equal(m.counters[:, :, 3], cols)
 
 
+@pytest.mark.parametrize("case", SEEDED_CASES)
+def test_reference_fixtures_at_production_settings(case):
+    """The kernels of 13..48 samples (mid-p; clusters of 2 and 4 on the 20,000- and 40,000-column genes), of more than
+    48 samples, and the long-gene tiers of the small-p kernel (streamed clusters of 4, 8 and 16 on genes of 40,000 to
+    300,000 columns; 149,579 kept columns through 17 nmf() calls) against the UNMODIFIED reference at its real
+    settings: nmf_iter = 100, 2-3 outer iterations.  Fixtures: oracle/gen_golden.py (seeded cases)."""
+    mats, reads, kwargs, ref = load_seeded_case(case)
+    m, est = _gpu_run(mats, reads, **kwargs)
+    _compare(m, None, ref)
+    np.testing.assert_allclose(np.array([e.sum(axis=1) for e in est]), ref["est_rowsum"], rtol=1e-7)
+    np.testing.assert_allclose(np.array([e.max(axis=1) for e in est]), ref["est_max"], rtol=1e-6)
+    w = ref["nmf_widths"]
+    np.testing.assert_array_equal(m.counters[:, :, 2], (w >= 0).sum(axis=2))
+    np.testing.assert_array_equal(m.counters[:, :, 3], np.where(w >= 0, w, 0).sum(axis=2))
+    clusters = sorted({int(b.plan.cluster) for b in m._engine.buckets})
+    if case == "seed_p48_long":
+        assert clusters == [1, 2, 4], clusters
+    if case == "seed_p12_long":
+        assert {4, 8, 16} <= set(clusters), clusters
+        assert any(int(b.plan.cluster) > 1 and int(b.plan.resident_cols) == 0 for b in m._engine.buckets)
+
+
+def test_single_matrix_methods_known_answers():
+    """rank_one_approx / nmf / ratio_svd / baseline_selection as single-matrix methods on the device path
+    (nmf.py:55-121, 189-372), against the reference's own outputs (tests/golden/kat.npz)."""
+    import os
+    from degnorm_b200 import GeneNMFOA
+    d = np.load(os.path.join(GOLDEN, "kat.npz"))
+    x = d["x"]
+    m = GeneNMFOA(nmf_iter=100)
+    K, E = m.nmf(x, factors=True)
+    assert K.shape == (3, 1) and E.shape == (1, 8) and (K >= 0).all() and (E >= 0).all()
+    np.testing.assert_allclose(K.ravel(), d["nmf_absK"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(K.dot(E), d["nmf_est"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(m.nmf(x), d["nmf_est"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(m.ratio_svd(x), d["ratio_svd_est"], rtol=0, atol=1e-9)
+    K1, E1 = GeneNMFOA.rank_one_approx(x)
+    u, s, vt = np.linalg.svd(x, full_matrices=False)
+    np.testing.assert_allclose(K1.dot(E1), s[0] * np.outer(u[:, 0], vt[0]), rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.linalg.norm(E1), 1.0, rtol=1e-12)
+    with pytest.raises(ValueError):
+        GeneNMFOA.rank_one_approx(x[:, :1])                     # svds(k=1) refuses min(shape) < 2 (nmf.py:63)
+    # a zero row is legal input for nmf() (svds handles it)
+    x0 = x.copy(); x0[1] = 0.0
+    Kz, Ez = m.nmf(x0, factors=True)
+    assert Kz[1, 0] == 0.0 and np.isfinite(Kz).all()
+
+
+def test_single_gene_baseline_selection_method():
+    """GeneNMFOA.baseline_selection(F) for one gene: unclipped rho, full-length estimate, flag -- against the oracle
+    (which the golden fixtures pin), with and without down-sampling (offset drawn from the global numpy stream)."""
+    from degnorm_b200 import GeneNMFOA
+    from degnorm_b200.synth import synth_numpy
+    from oracle import nmfoa_oracle as orc
+    mats, _ = synth_numpy(3, 5, 31, lengths=np.array([700, 1500, 90]), jitter=1e-6)
+    for rate in (1, 4):
+        kw = dict(nmf_iter=60, downsample_rate=rate)
+        m = GeneNMFOA(**kw)
+        m.p = 5
+        prm = orc.Params(rank1="gram", **kw)
+        for F in mats:
+            np.random.seed(5)
+            rho, est, ran = m.baseline_selection(F)
+            np.random.seed(5)
+            start = int(np.random.choice(rate)) if rate > 1 else 0
+            r_ref, e_ref, ran_ref = orc.baseline_selection(F, prm, start, {})
+            assert ran == ran_ref
+            np.testing.assert_allclose(rho, r_ref, rtol=0, atol=1e-8)
+            np.testing.assert_allclose(est, e_ref, rtol=1e-7, atol=1e-7)
+
+
+def test_run_logs_the_reference_lines(caplog):
+    """nmf.py:537-538, 571-572, 592-593: same log lines, same order."""
+    import logging
+    from degnorm_b200.synth import synth_numpy
+    mats, reads = synth_numpy(5, 4, 12, lengths=np.array([300, 420, 700, 256, 512]), jitter=1e-6)
+    with caplog.at_level(logging.INFO):
+        m, _ = _gpu_run(mats, reads, degnorm_iter=2, nmf_iter=20)
+    msgs = [r.getMessage() for r in caplog.records]
+    assert msgs[0].startswith("Initial sequencing depth scale factors -- \n\t")
+    assert msgs[1] == "DegNorm iteration 1 -- %d genes sent through baseline selection" % m.ran_baseline_selection[:, 0].sum()
+    assert msgs[2].startswith("DegNorm iteration 1 -- sequencing depth scale factors: \n\t")
+    assert msgs[4].startswith("DegNorm iteration 2 -- sequencing depth scale factors: \n\t")
+    assert msgs[4].endswith(", ".join(str(v) for v in m.scale_factors))
+
+
+def test_non_current_device_with_lazy_estimates():
+    """GeneNMFOA(device='cuda:1', return_estimates='lazy') while cuda:0 is current: the estimate launches that
+    follow run() must go to the engine's device (skipped on a single-GPU box)."""
+    import torch
+    from degnorm_b200.synth import synth_numpy
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    mats, reads = synth_numpy(6, 4, 9, lengths=np.array([300, 420, 700, 256, 512, 900]), jitter=1e-6)
+    torch.cuda.set_device(0)
+    lazy, est_lazy = _gpu_run(mats, reads, degnorm_iter=2, nmf_iter=30, device="cuda:1", return_estimates="lazy")
+    eager, est = _gpu_run(mats, reads, degnorm_iter=2, nmf_iter=30, device="cuda:0")
+    assert torch.cuda.current_device() == 0
+    for k in range(len(mats)):
+        np.testing.assert_array_equal(est_lazy[k], est[k])
+    np.testing.assert_array_equal(lazy.rho, eager.rho)
+
+
 def test_integer_count_ties_are_the_only_mismatches():
     """Integer counts make `max_i F_ij/s_i > 0.1*max(F/s)` (nmf.py:76) an exact tie for columns whose maximum is
     one tenth of the matrix maximum; the reference's own answer then depends on the last bit of its scale factors
@@ -86,11 +189,13 @@ def _oracle(mats, reads, **kwargs):
     (2, 6, dict(degnorm_iter=2, nmf_iter=30)),
     (5, 8, dict(degnorm_iter=2, nmf_iter=50)),
     (12, 6, dict(degnorm_iter=2, nmf_iter=40, downsample_rate=4)),
-    (17, 5, dict(degnorm_iter=1, nmf_iter=30)),
-    (48, 4, dict(degnorm_iter=1, nmf_iter=25)),
-    (70, 3, dict(degnorm_iter=1, nmf_iter=10)),
-    (130, 2, dict(degnorm_iter=1, nmf_iter=6)),
-    (200, 2, dict(degnorm_iter=1, nmf_iter=5)),       # more Gram tiles than threads (multi-set path)
+    (17, 5, dict(degnorm_iter=2, nmf_iter=100)),
+    (33, 4, dict(degnorm_iter=2, nmf_iter=100)),
+    (48, 4, dict(degnorm_iter=2, nmf_iter=100)),
+    (70, 3, dict(degnorm_iter=2, nmf_iter=100)),
+    (130, 2, dict(degnorm_iter=2, nmf_iter=100)),
+    (200, 2, dict(degnorm_iter=2, nmf_iter=100)),
+    (256, 2, dict(degnorm_iter=1, nmf_iter=100)),
 ])
 def test_against_oracle_across_sample_counts(p, n_genes, kwargs):
     from degnorm_b200.synth import synth_numpy
