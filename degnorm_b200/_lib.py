@@ -56,6 +56,8 @@ _SIGS = {
     "dn_init_sums": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P]),
     "dn_init_apply": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "dn_sums_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
+    "dn_probe_fp64": (C.c_int64, [C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    "dn_probe_lds": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
 }
 EXPORTS = sorted(_SIGS)
 

@@ -223,7 +223,9 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
         if (mode != MODE_BS || prm->p <= 12 || prm->p > MID_P) return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
         a.pp = MID_P;
         a.ws_stride = mid_slab_doubles(plan->ws_cols);
-        return plan->threads == 128 ? dn_launch_mid4(a, plan, st) : dn_launch_mid8(a, plan, st);
+        if (plan->threads == 128) return dn_launch_mid4(a, plan, st);
+        if (plan->threads == 256) return dn_launch_mid8(a, plan, st);
+        return dn_launch_midws(a, plan, st);
     }
     if (plan->tile == 0) {
         // small-p path (baseline selection only)
@@ -283,13 +285,15 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         // ---- mid-p path (13..48 samples): streamed kernel, optional cluster per gene
         int cl = cluster > 1 ? cluster : 1;
         if (cl != 1 && cl != 2 && cl != 4 && cl != 8 && cl != 16) return fail(DN_ERR_INVALID, "cluster must be 1, 2, 4, 8 or 16%s");
-        // warps = 4: two 4-warp CTAs per SM (one CTA's reduction and eigen-solve overlap the other's stream)
+        // warps = 4: two 4-warp CTAs per SM; warps = 8: one 8-warp CTA per SM, every warp updates and accumulates;
+        // anything else (default): the warp-specialised instantiation, 8 Gram warps + 4 update warps
         const int nw = warps == 4 ? 4 : MID_WARPS;
+        const int na = (warps == 4 || warps == 8) ? 0 : MID_UPD_WARPS;
         const int chunk = mid_chunk(nw);
         long long share = (max_cols + cl - 1) / cl;
         share = (share + chunk - 1) / chunk * chunk;
         plan->tile = 6;
-        plan->threads = nw * 32;
+        plan->threads = (nw + na) * 32;
         plan->cluster = cl;
         plan->resident_cols = 0;
         plan->smem_bytes = (int32_t)(mid_carve(nw).total * 8);

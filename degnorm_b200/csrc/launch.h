@@ -111,10 +111,12 @@ __host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols
 }
 
 // ---- mid-p kernel (13 <= p <= 48; nmfoa_mid.cuh): streamed, CTA-level TMA ring of (8 x warps)-column chunks ------
-// Two instantiations: 8 warps (one CTA per SM, 64-column chunks) and 4 warps (two CTAs per SM, 32-column chunks:
-// one CTA's reduction / eigen-solve / barriers overlap the other CTA's stream).
+// Three instantiations: warp-specialised (default: 8 Gram warps + 4 update warps, one CTA per SM, 64-column chunks,
+// no block barrier inside a pass), 8 warps (one CTA per SM, every warp updates and accumulates, one block barrier per
+// chunk) and 4 warps (two such CTAs per SM, 32-column chunks).
 constexpr int MID_P = 48;             // samples padded to this
-constexpr int MID_WARPS = 8;          // default warps per CTA
+constexpr int MID_WARPS = 8;          // Gram warps per CTA
+constexpr int MID_UPD_WARPS = 2;      // update warps of the warp-specialised instantiation
 constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
 constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
 __host__ __device__ constexpr int mid_chunk(int nw) { return 8 * nw; }   // columns per ring stage
@@ -131,7 +133,7 @@ __host__ __device__ inline MidCarve mid_carve(int nw) {
     c.ibuf = o;  o += 16;
     c.lw = o;    o += DN_MAX_BINS / 2;
     c.tab = o;   o += 32;
-    c.mbar = o;  o += 4;                        // MID_RING mbarriers
+    c.mbar = o;  o += 8;                        // MID_RING "chunk landed" + MID_RING "chunk updated" mbarriers
     const long long stage = 2ll * mid_chunk(nw) * (MID_P + 2);
     // 4-warp CTAs (two per SM): G lives in the ring's last stage, which is free between two passes (the ring is
     // primed with chunks 0 and 1 only) -- the eigen-solve is the only user of G
@@ -152,6 +154,7 @@ __host__ __device__ inline long long mid_slab_doubles(long long ws_cols) {
 // launchers (each defined in its own translation unit)
 int dn_launch_mid8(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_mid4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
+int dn_launch_midws(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_tiled(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_small4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_small8(const KArgs &a, const dn_plan *plan, cudaStream_t st);

@@ -40,11 +40,23 @@ namespace {
 // one thread after the chunk barrier) instead of six 128-bit stores per thread in phase A.  The kernel is bound by
 // its load/store pipe: on the 8-warp instantiation this took C3 from 0.52 to 0.59 of the HBM roofline; the 4-warp
 // one (32-column chunks, loads only one chunk ahead of their use) measured no gain and keeps per-thread stores.
-constexpr int MNW = MID_NW;               // warps per CTA (8: one CTA per SM; 4: two CTAs per SM)
+#ifndef MID_NA
+#define MID_NA 0
+#endif
+// MID_NA > 0: warp-specialised instantiation.  Warps 0 .. MNW-1 ("B warps") only accumulate the Gram matrix, warps
+// MNW .. MNW+MNA-1 ("A warps") only run the multiplier update one chunk ahead of them; nobody waits at a block barrier
+// inside a pass (see gram_mid_ws).
+constexpr int MNW = MID_NW;               // Gram warps per CTA (8: one CTA per SM; 4: two CTAs per SM)
+constexpr int MNA = MID_NA;               // update warps (warp-specialised instantiation only)
 constexpr int MP = MID_P;                 // padded samples
 constexpr int MCS = MID_P + 2;            // column stride (doubles)
-constexpr int MNT = MNW * 32;             // threads
-constexpr int MCH = mid_chunk(MNW);       // columns per chunk (4 lanes per column in phase A)
+constexpr int MNT = (MNW + MNA) * 32;     // threads
+constexpr int MNWT = MNW + MNA;           // warps
+constexpr int MCH = mid_chunk(MNW);       // columns per chunk
+constexpr int MCPR = MNT / 4;             // columns per CTA step where 4 lanes share a column (scan-type passes)
+constexpr int IB_WCOUNT = 1;              // ibuf slots: [0] queue ticket, [1 .. 12] per-warp counts, [20] eigen flag,
+constexpr int IB_EIG = 20;                //             [24 .. 26] consumers done with a ring stage
+constexpr int IB_FREE = 24;
 constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
 constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
 
@@ -61,6 +73,9 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
                      smem_u32(smem_dst)),
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     asm volatile(
@@ -109,6 +124,7 @@ struct MGene {
     bool primed;
     unsigned long long *mbar;                      // MID_RING mbarriers (one per ring stage)
     unsigned use0, use1, use2;                      // completed fills per stage (phase parity of its mbarrier)
+    unsigned seq;                                   // warp-specialised instantiation: ring chunks consumed so far
 };
 
 __device__ __forceinline__ int mlstart(const MGene &g, int k) {
@@ -149,6 +165,72 @@ __device__ void mclu_allsum(MGene &g, const double *vals, int n, double *out) {
         out[k] = s;
     }
     g.xpar ^= 1;
+    __syncthreads();
+}
+
+// ---- end of a pass: the Gram warps' partial sums -> CTA sum -> cluster sum -> square G in shared memory -----------
+__device__ void gram_finish(MGene &g, double (&acc)[6][8]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
+    double *mine = g.buf + (long long)(warp & 3) * MNE + lane * 48;
+    for (int half = MNW / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half && lane < MNTILE) {
+            double *dst = g.buf + (long long)(warp - half) * MNE + lane * 48;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; q += 2)
+                    *reinterpret_cast<double2 *>(dst + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+        }
+        __syncthreads();
+        if (warp < half && lane < MNTILE) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int q = 0; q < 8; q += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(mine + r * 8 + q);
+                    acc[r][q] += t.x;
+                    acc[r][q + 1] += t.y;
+                }
+        }
+        __syncthreads();
+    }
+    if (warp == 0 && lane < MNTILE) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = 0; q < 8; q += 2)
+                *reinterpret_cast<double2 *>(g.buf + lane * 48 + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+    }
+    __syncthreads();
+    // ---- cluster sum (rank order) and scatter into the square G
+    const double *src = g.buf;
+    if (g.csize > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        double *slot = g.slots + (long long)g.xpar * MNE;
+        for (int e = tid; e < MNE; e += MNT) slot[e] = g.buf[e];
+        __threadfence();
+        cl.sync();
+        src = nullptr;
+    }
+    const double *first = g.slots - (long long)g.crank * g.slot_stride + (long long)g.xpar * MNE;
+    for (int e = tid; e < MNE; e += MNT) {
+        double s;
+        if (src) {
+            s = src[e];
+        } else {
+            s = 0.0;
+            for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + e);
+        }
+        const int t = e / 48, rq = e - t * 48;
+        const int c0t = g.tab[2 * t + 1], q = rq & 7;
+        const int i = g.tab[2 * t] + rq / 8, j = c0t + 2 * (((q >> 1) + (c0t >> 4)) & 3) + (q & 1);
+        if (i <= j) {
+            g.G[i * MP + j] = s;
+            g.G[j * MP + i] = s;
+        }
+    }
+    if (g.csize > 1) g.xpar ^= 1;
     __syncthreads();
 }
 
@@ -310,67 +392,202 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
 #pragma unroll
         for (int q = 0; q < MID_RING - 1; ++q) issue(q, true);
     }
-    // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
-    double *mine = g.buf + (long long)(warp & 3) * MNE + lane * 48;
-    for (int half = MNW / 2; half >= 1; half >>= 1) {
-        if (warp >= half && warp < 2 * half && lane < MNTILE) {
-            double *dst = g.buf + (long long)(warp - half) * MNE + lane * 48;
-#pragma unroll
-            for (int r = 0; r < 6; ++r)
-#pragma unroll
-                for (int q = 0; q < 8; q += 2)
-                    *reinterpret_cast<double2 *>(dst + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+    gram_finish(g, acc);
+}
+
+// ---- the same pass, warp-specialised (MID_NA > 0) ------------------------------------------------------------------
+// Roles.  B warps (0 .. MNW-1) own the Gram accumulators and nothing else; A warps (MNW ..) run the multiplier update on
+// the chunk that landed last, one chunk ahead of the B warps, and send the updated M back to the slab (one bulk store
+// per A warp and chunk: its own 16 columns).  Hand-over per ring stage:
+//     full[s]  (mbarrier, TMA transaction bytes) : chunk landed                        -> A warps (B warps on the first pass)
+//     upd[s]   (mbarrier, every A thread arrives): M of the chunk is final in the stage -> B warps
+//     free[s]  (shared counter)                  : B warps are done reading the stage and the A warps' bulk stores have
+//                                                  read it; whoever arrives LAST requests chunk ch + RING into it
+// so no thread ever waits for a stage to drain, and no block barrier is taken inside a pass: the update of chunk k + 1
+// (latency-bound: shared loads -> dot product -> two shuffles -> 36 FMAs -> stores) overlaps the Gram FMAs of chunk k
+// (throughput-bound on the FP64 pipe and the shared-memory wavefronts) on the same SM sub-partitions.
+template <bool UPDATE>
+__device__ void gram_mid_ws(const KArgs &a, MGene &g, bool prime_next) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = g.n_cur;
+    const int nchunk = (n + MCH - 1) / MCH;
+    constexpr int STG = 2 * MCH * MCS;                     // doubles per ring stage (M then x)
+    constexpr unsigned CHB = MCH * MCS * 8;                // bytes of one array's chunk
+    unsigned long long *full = g.mbar, *upd = g.mbar + MID_RING;
+    volatile int *freec = g.ibuf + IB_FREE;
+    const bool is_b = warp < MNW;
+    // Ring bookkeeping: chunks are numbered through the whole kernel (g.seq = chunks consumed so far, the same in
+    // every thread); chunk number k lives in stage k % RING and is the (k / RING)-th fill of it, which gives the
+    // phase parity of the stage's two mbarriers.
+    const unsigned seq0 = g.seq;
+
+    // request chunk ch of this pass (caller: the stage is free, the slab holds the data)
+    auto issue = [&](int ch, bool with_x) {
+        const unsigned st = (seq0 + (unsigned)ch) % MID_RING;
+        double *dst = g.ring + st * STG;
+        fence_proxy_async_smem();
+        mbar_expect_tx(full + st, with_x ? 2 * CHB : CHB);
+        bulk_g2s(dst, g.M + (long long)ch * (MCH * MCS), CHB, full + st);
+        if (with_x) bulk_g2s(dst + MCH * MCS, g.X + (long long)ch * (MCH * MCS), CHB, full + st);
+    };
+    // one consumer (a B warp, or an A warp whose bulk store has read the stage) is done with chunk ch; called by lane 0
+    auto release = [&](int ch) {
+        if (ch + MID_RING < nchunk) {
+            const unsigned st = (seq0 + (unsigned)ch) % MID_RING;
+            __threadfence_block();
+            const int old = atomicAdd(const_cast<int *>(freec + st), 1);
+            if (old == MNW + MNA - 1) {
+                freec[st] = 0;
+                __threadfence_block();
+                issue(ch + MID_RING, UPDATE);
+            }
         }
-        __syncthreads();
-        if (warp < half && lane < MNTILE) {
+    };
+    if (!g.primed) {
+        if (tid == 0)
+            for (int q = 0; q < MID_RING && q < nchunk; ++q) issue(q, UPDATE);
+    }
+    double acc[6][8];
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+    for (int r = 0; r < 6; ++r)
 #pragma unroll
-                for (int q = 0; q < 8; q += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(mine + r * 8 + q);
-                    acc[r][q] += t.x;
-                    acc[r][q + 1] += t.y;
+        for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
+
+    if (is_b) {
+        // -------------------------------------------------------------------------------------------- Gram warps
+        const int tr0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane) : -1;
+        const int tc0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane + 1) : 0;
+        const int rot = tc0 >> 4;
+        const int uo0 = tc0 + 2 * ((0 + rot) & 3), uo1 = tc0 + 2 * ((1 + rot) & 3), uo2 = tc0 + 2 * ((2 + rot) & 3),
+                  uo3 = tc0 + 2 * ((3 + rot) & 3);
+#pragma unroll 1
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const unsigned k = seq0 + (unsigned)ch, st = k % MID_RING;
+            mbar_wait(upd + st, (k / MID_RING) & 1u);
+            const double *sM = g.ring + st * STG;
+            const int ncol = min(MCH, n - ch * MCH);
+            if (tr0 >= 0) {
+                int cc = warp * (MCH / MNW);
+                const int cend = min(ncol, cc + MCH / MNW);
+#define MID_LOADP(S, col)                                                                   \
+    {                                                                                       \
+        const double *mc_ = sM + (col) * MCS;                                               \
+        S##a0 = *reinterpret_cast<const double2 *>(mc_ + tr0);                              \
+        S##a1 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 2);                          \
+        S##a2 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 4);                          \
+        S##u0 = *reinterpret_cast<const double2 *>(mc_ + uo0);                              \
+        S##u1 = *reinterpret_cast<const double2 *>(mc_ + uo1);                              \
+        S##u2 = *reinterpret_cast<const double2 *>(mc_ + uo2);                              \
+        S##u3 = *reinterpret_cast<const double2 *>(mc_ + uo3);                              \
+    }
+#define MID_FMAP(S)                                                                         \
+    {                                                                                       \
+        const double ar_[6] = {S##a0.x, S##a0.y, S##a1.x, S##a1.y, S##a2.x, S##a2.y};       \
+        const double uc_[8] = {S##u0.x, S##u0.y, S##u1.x, S##u1.y, S##u2.x, S##u2.y, S##u3.x, S##u3.y}; \
+        _Pragma("unroll") for (int r = 0; r < 6; ++r)                                       \
+            _Pragma("unroll") for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar_[r], uc_[q], acc[r][q]); \
+    }
+                double2 Aa0, Aa1, Aa2, Au0, Au1, Au2, Au3, Ba0, Ba1, Ba2, Bu0, Bu1, Bu2, Bu3;
+#pragma unroll 1
+                for (; cc + 1 < cend; cc += 2) {
+                    MID_LOADP(A, cc);
+                    MID_LOADP(B, cc + 1);
+                    MID_FMAP(A);
+                    MID_FMAP(B);
                 }
+                if (cc < cend) {
+                    MID_LOADP(A, cc);
+                    MID_FMAP(A);
+                }
+#undef MID_LOADP
+#undef MID_FMAP
+            }
+            __syncwarp();
+            if (lane == 0) release(ch);
         }
-        __syncthreads();
-    }
-    if (warp == 0 && lane < MNTILE) {
+    } else {
+        // -------------------------------------------------------------------------------------------- update warps
+        const int aw = warp - MNW;                            // this warp's columns of a chunk: [CPA aw, CPA (aw + 1))
+        constexpr int CPA = MCH / (MNA > 0 ? MNA : 1);
+        const int q4 = lane & 3;
+        const double c = a.c;
+        double vq[12];
+        if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
+#pragma unroll 1
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const unsigned k = seq0 + (unsigned)ch, st = k % MID_RING;
+            mbar_wait(full + st, (k / MID_RING) & 1u);
+            double *sM = g.ring + st * STG;
+            const int ncol = min(MCH, n - ch * MCH);
+            if constexpr (UPDATE) {
+#pragma unroll 1
+                for (int rd = 0; rd < CPA / 8; ++rd) {
+                    const int cc = aw * CPA + rd * 8 + (lane >> 2);
+                    const bool act = cc < ncol;
+                    double m[12], x[12];
+                    double tp = 0.0;
+                    if (act) {
+                        ld12(sM + cc * MCS + 12 * q4, m);
+                        ld12(sM + MCH * MCS + cc * MCS + 12 * q4, x);
+                        double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+                        for (int i = 0; i < 12; i += 2) { t0 = fma(vq[i], m[i], t0); t1 = fma(vq[i + 1], m[i + 1], t1); }
+                        tp = t0 + t1;
+                    }
+                    double t = tp;
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    if (act) {
 #pragma unroll
-            for (int q = 0; q < 8; q += 2)
-                *reinterpret_cast<double2 *>(g.buf + lane * 48 + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
-    }
-    __syncthreads();
-    // ---- cluster sum (rank order) and scatter into the square G
-    const double *src = g.buf;
-    if (g.csize > 1) {
-        cg::cluster_group cl = cg::this_cluster();
-        double *slot = g.slots + (long long)g.xpar * MNE;
-        for (int e = tid; e < MNE; e += MNT) slot[e] = g.buf[e];
-        __threadfence();
-        cl.sync();
-        src = nullptr;
-    }
-    const double *first = g.slots - (long long)g.crank * g.slot_stride + (long long)g.xpar * MNE;
-    for (int e = tid; e < MNE; e += MNT) {
-        double s;
-        if (src) {
-            s = src[e];
-        } else {
-            s = 0.0;
-            for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + e);
+                        for (int i = 0; i < 12; ++i) {
+                            const double res = fma(vq[i], t, -x[i]);
+                            const double w = fma(-c, res, m[i] - x[i]);
+                            m[i] = fma(0.5, w + fabs(w), x[i]);
+                        }
+                        st12(sM + cc * MCS + 12 * q4, m);
+                    }
+                }
+                fence_proxy_async_smem();                     // the stage is read by this warp's bulk store below
+            }
+            mbar_arrive(upd + st);                            // (release: the Gram warps may read the stage)
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (UPDATE) {
+                    const int c0 = aw * CPA, nmine = min(CPA, ncol - c0);
+                    if (nmine > 0)
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(
+                                         g.M + ((long long)ch * MCH + c0) * MCS),
+                                     "r"(smem_u32(sM + c0 * MCS)), "r"((unsigned)(nmine * MCS * 8))
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+                    bulk_wait_read<1>();                      // the store of the previous chunk has read its stage
+                    if (ch >= 1) release(ch - 1);
+                } else {
+                    release(ch);
+                }
+            }
         }
-        const int t = e / 48, rq = e - t * 48;
-        const int c0t = g.tab[2 * t + 1], q = rq & 7;
-        const int i = g.tab[2 * t] + rq / 8, j = c0t + 2 * (((q >> 1) + (c0t >> 4)) & 3) + (q & 1);
-        if (i <= j) {
-            g.G[i * MP + j] = s;
-            g.G[j * MP + i] = s;
+        if constexpr (UPDATE) {
+            if (lane == 0) bulk_wait_all();                   // the slab holds this warp's columns of the new M
         }
     }
-    if (g.csize > 1) g.xpar ^= 1;
+    g.seq = seq0 + (unsigned)nchunk;
+    fence_proxy_async();
     __syncthreads();
+    g.primed = prime_next;
+    if (prime_next && tid == 0) {
+        // the next pass is an update pass over the same columns: request its first chunks now (they travel while the
+        // partial Grams are reduced and the eigen-solve runs)
+        for (int q = 0; q < MID_RING && q < nchunk; ++q) {
+            const unsigned st = (g.seq + (unsigned)q) % MID_RING;
+            double *dst = g.ring + st * STG;
+            fence_proxy_async_smem();
+            mbar_expect_tx(full + st, 2 * CHB);
+            bulk_g2s(dst, g.M + (long long)q * (MCH * MCS), CHB, full + st);
+            bulk_g2s(dst + MCH * MCS, g.X + (long long)q * (MCH * MCS), CHB, full + st);
+        }
+    }
+    gram_finish(g, acc);
 }
 
 // ---- top eigenvector of G (MP x MP, shared); same rules as eig_warp in nmfoa_tiled.cu -----------------------------
@@ -447,10 +664,10 @@ __device__ int eig_mid_block(const double *G, int p, double *v, double *part, in
 }
 
 __device__ void eig_mid(const KArgs &a, MGene &g, bool cold) {
-    const int s0 = eig_mid_block(g.G, a.p, g.v, g.buf, g.ibuf + 12, cold);
+    const int s0 = eig_mid_block(g.G, a.p, g.v, g.buf, g.ibuf + IB_EIG, cold);
     g.eig_steps += s0;
     __syncthreads();
-    const int conv = g.ibuf[12];
+    const int conv = g.ibuf[IB_EIG];
     __syncthreads();
     if (conv != 1) {                               // uniform across the CTA (and the cluster: same G everywhere)
         const int s = eig_squaring<MNT>(g.G, MP, a.p, g.v, g.red, g.B0, g.B0 + MP * MP, conv == 2);
@@ -471,9 +688,9 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
 #pragma unroll
     for (int i = 0; i < 12; ++i) { sF[i] = 0.0; sC[i] = 0.0; }
     // 4 lanes per column again; whole warps iterate together (64 columns per CTA step)
-    const int nround = (n + MCH - 1) / MCH;
+    const int nround = (n + MCPR - 1) / MCPR;
     for (int rd = 0; rd < nround; ++rd) {
-        const int col = rd * MCH + (tid >> 2);
+        const int col = rd * MCPR + (tid >> 2);
         double m[12], x[12];
         double tp = 0.0;
         if (col < n) {
@@ -535,12 +752,12 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
     if (tid < 2 * MP) {
         const int which = tid / MP, i = tid - which * MP;
         double s = 0.0;
-        for (int w = 0; w < MNW; ++w) s += g.buf[(w * 2 + which) * MP + i];
-        g.buf[MNW * 2 * MP + tid] = s;              // [0, MP): rsF, [MP, 2MP): rsC
+        for (int w = 0; w < MNWT; ++w) s += g.buf[(w * 2 + which) * MP + i];
+        g.buf[MNWT * 2 * MP + tid] = s;             // [0, MP): rsF, [MP, 2MP): rsC
     }
-    if (tid == 0) { g.buf[MNW * 2 * MP + 2 * MP] = sum_t_l; g.buf[MNW * 2 * MP + 2 * MP + 1] = sum_t2_l; }
+    if (tid == 0) { g.buf[MNWT * 2 * MP + 2 * MP] = sum_t_l; g.buf[MNWT * 2 * MP + 2 * MP + 1] = sum_t2_l; }
     __syncthreads();
-    double *vals = g.buf + MNW * 2 * MP;            // 2 MP + 2 values
+    double *vals = g.buf + MNWT * 2 * MP;           // 2 MP + 2 values
     mclu_allsum(g, vals, 2 * MP + 2, vals);
     const double sum_t = vals[2 * MP], sum_t2 = vals[2 * MP + 1];
     const double sigma = sqrt(sum_t2);
@@ -570,16 +787,29 @@ __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res,
     __syncthreads();
     const int T = a.nmf_iter;
     g.primed = false;
-    gram_mid<false>(a, g, T > 0);
-    eig_mid(a, g, true);
-    for (int it = 0; it < T; ++it) {
-        gram_mid<true>(a, g, it + 1 < T);
-        eig_mid(a, g, false);
+    if constexpr (MNA > 0) {
+        gram_mid_ws<false>(a, g, T > 0);
+        eig_mid(a, g, true);
+        for (int it = 0; it < T; ++it) {
+            gram_mid_ws<true>(a, g, it + 1 < T);
+            eig_mid(a, g, false);
+        }
+    } else {
+        gram_mid<false>(a, g, T > 0);
+        eig_mid(a, g, true);
+        for (int it = 0; it < T; ++it) {
+            gram_mid<true>(a, g, it + 1 < T);
+            eig_mid(a, g, false);
+        }
     }
     final_pass_mid(a, g, first, want_res, e_first_g);
 }
 
+#if MID_NA > 0
+__global__ void __maxnreg__(200) nmfoa_mid_kernel(const KArgs a) {      // 320 threads x 200 registers: one CTA per SM
+#else
 __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const KArgs a) {
+#endif
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p;
@@ -599,8 +829,12 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
     g.ring = smem + cv.ring;
     g.mbar = reinterpret_cast<unsigned long long *>(smem + cv.mbar);
     g.use0 = g.use1 = g.use2 = 0;
+    g.seq = 0;
     if (tid == 0) {
         for (int q = 0; q < MID_RING; ++q) mbar_init(g.mbar + q, 1);
+        // warp-specialised instantiation: "updated" barriers (every update thread arrives) and the consumer counters
+        for (int q = 0; q < MID_RING; ++q) mbar_init(g.mbar + MID_RING + q, MNA > 0 ? MNA * 32 : 1);
+        for (int q = 0; q < MID_RING; ++q) g.ibuf[IB_FREE + q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     cg::cluster_group cl = cg::this_cluster();
@@ -682,7 +916,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
         } else {
             // keep + compact (one thread per candidate column; the 48 scaled values go straight to the slab)
             int running = 0;
-            int *wcount = g.ibuf + 1;
+            int *wcount = g.ibuf + IB_WCOUNT;
             for (int kb = k_lo; kb < k_hi; kb += MNT) {
                 const int k = kb + tid;
                 bool keep = false;
@@ -698,7 +932,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
                 __syncthreads();
                 int pre = running, tot = 0;
 #pragma unroll
-                for (int q = 0; q < MNW; ++q) {
+                for (int q = 0; q < MNWT; ++q) {
                     const int cq = wcount[q];
                     if (q < warp) pre += cq;
                     tot += cq;
@@ -735,7 +969,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
                 double rs[12];
 #pragma unroll
                 for (int i = 0; i < 12; ++i) rs[i] = 0.0;
-                for (int col = tid >> 2; col < g.n0; col += MNT / 4) {
+                for (int col = tid >> 2; col < g.n0; col += MCPR) {
                     double x[12];
                     ld12(g.X + (long long)col * MCS + 12 * q4, x);
 #pragma unroll
@@ -752,7 +986,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
                 __syncthreads();
                 if (tid < MP) {
                     double s = 0.0;
-                    for (int w2 = 0; w2 < MNW; ++w2) s += g.buf[w2 * MP + tid];
+                    for (int w2 = 0; w2 < MNWT; ++w2) s += g.buf[w2 * MP + tid];
                     g.rs0[tid] = s;
                 }
                 __syncthreads();
@@ -805,7 +1039,7 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
                     }
                     if (!(rmax > 0.1)) break;
                     ran = 1;
-                    for (int k = warp; k < g.nalive; k += MNW) {
+                    for (int k = warp; k < g.nalive; k += MNWT) {
                         const int wl = g.lw[g.alive[k]];
                         const double *rr = g.resb + mlstart(g, k);
                         double s = 0.0;

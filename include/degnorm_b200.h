@@ -185,6 +185,15 @@ int dn_init_apply(const double *sums, const double *reads, int32_t n_genes, int3
 /* workspace bytes dn_outer_sums / dn_init_sums need */
 int64_t dn_sums_workspace_bytes(int32_t n_genes, int32_t p);
 
+/* ---- measurement probes (not on the product path; csrc/probes.cu) ------------------------------------------------
+ * SURVEY.md section 8(d) asks for an FP64 peak measured on the box: dn_probe_fp64 launches `ctas` CTAs of 256 threads,
+ * each thread 64 * iters DFMAs in 16 independent chains, writes every CTA's SM clock cycles to cycles[ctas] and returns
+ * the number of DFMAs issued.  dn_probe_lds does the same for 128-bit shared-memory loads with a lane -> address
+ * pattern (0: 32 distinct conflict-free, 1: one address, 2: one address per quarter-warp, 3: every quarter-warp the same
+ * 128 bytes, ...) and returns the warp-level loads per CTA.  seed: 2 doubles, sink: 1 double (device). */
+int64_t dn_probe_fp64(int32_t ctas, int32_t iters, const double *seed, double *sink, int64_t *cycles, void *stream);
+int64_t dn_probe_lds(int32_t ctas, int32_t pattern, int32_t iters, double *sink, int64_t *cycles, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -284,12 +284,13 @@ def test_cluster_path_equals_single_cta_path(p, cluster, streamed):
     np.testing.assert_allclose(a["est"], b["est"], rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("p,cluster,warps", [(17, 1, 8), (48, 1, 8), (48, 4, 8), (30, 16, 8),
-                                             (48, 1, 4), (17, 2, 4), (48, 4, 4), (30, 16, 4)])
+@pytest.mark.parametrize("p,cluster,warps", [(17, 1, 0), (48, 1, 0), (48, 2, 0), (48, 4, 0), (30, 16, 0),
+                                             (48, 1, 8), (30, 16, 8), (48, 1, 4), (17, 2, 4), (30, 16, 4)])
 def test_mid_kernel_equals_tiled_kernel(p, cluster, warps):
-    """13..48 samples: the streamed mid-p kernel (8 warps per CTA, or two 4-warp CTAs per SM; optionally one
-    cluster per gene) against the generic tiled kernel on the same genes: identical decisions and call sequences,
-    DI equal to rounding."""
+    """13..48 samples: the streamed mid-p kernel (warps = 0: the default warp-specialised instantiation, 8 Gram warps
+    + 2 update warps; 8: every warp updates and accumulates; 4: two 4-warp CTAs per SM; optionally one cluster per
+    gene) against the generic tiled kernel on the same genes: identical decisions and call sequences, DI equal to
+    rounding."""
     import torch
     from degnorm_b200.engine import Params, ShardEngine
     from degnorm_b200.packing import pack_coverage
@@ -306,7 +307,7 @@ def test_mid_kernel_equals_tiled_kernel(p, cluster, warps):
         eng.force_cluster = cluster if (use_mid and cluster > 1) else 0
         eng.load(flat.cuda(), off, torch.from_numpy(reads).cuda())
         assert all((int(b.plan.tile) == 6) == use_mid for b in eng.buckets)
-        assert not use_mid or all(int(b.plan.threads) == 32 * warps for b in eng.buckets)
+        assert not use_mid or all(int(b.plan.threads) == (320 if warps == 0 else 32 * warps) for b in eng.buckets)
         o = eng.run(None, want_estimates=True)
         torch.cuda.synchronize()
         outs.append({k: v.cpu().numpy() for k, v in o.items() if torch.is_tensor(v)})

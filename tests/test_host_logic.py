@@ -289,9 +289,9 @@ def test_device_coverage_handle_filters_like_filter_genes_on_host_tensors():
 
 
 def test_mid_kernel_plans_are_pure_host_arithmetic():
-    """dn_make_plan for 13..48 samples (no device call): the 8-warp instantiation takes one CTA per SM with a
-    3 x 51.2 KB ring, the 4-warp one fits two CTAs per SM (G parked in the free ring stage); workspace columns are
-    whole chunks; clusters divide the CTA count."""
+    """dn_make_plan for 13..48 samples (no device call): the default warp-specialised instantiation (8 Gram warps +
+    2 update warps) and the 8-warp one take one CTA per SM with a 3 x 51.2 KB ring, the 4-warp one fits two CTAs per
+    SM (G parked in the free ring stage); workspace columns are whole chunks; clusters divide the CTA count."""
     import ctypes as C
     from degnorm_b200 import _lib
     from degnorm_b200.engine import Params
@@ -304,8 +304,11 @@ def test_mid_kernel_plans_are_pure_host_arithmetic():
         rc = lib.dn_make_plan(C.byref(prm), max_cols, n_work, 0, 0, warps, cluster, sm, smem, C.byref(pl))
         assert rc == 0, lib.dn_last_error()
         return pl
-    p8 = plan(5000, 10000, 0, 1)
+    pw = plan(5000, 10000, 0, 1)
+    assert (pw.tile, pw.threads, pw.cluster, pw.ctas) == (6, 320, 1, 148)
+    p8 = plan(5000, 10000, 8, 1)
     assert (p8.tile, p8.threads, p8.cluster, p8.ctas) == (6, 256, 1, 148)
+    assert (pw.smem_bytes, pw.ws_cols, pw.ws_bytes) == (p8.smem_bytes, p8.ws_cols, p8.ws_bytes)
     assert p8.smem_bytes <= smem and 2 * (p8.smem_bytes + 1024) > smem          # one CTA per SM
     assert p8.ws_cols == 5056 and p8.ws_cols % 64 == 0
     p4 = plan(5000, 10000, 4, 1)
