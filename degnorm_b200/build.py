@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SRC = [os.path.join(CSRC, f) for f in ("abi.cu", "nmfoa_tiled.cu", "nmfoa_small_p4.cu", "nmfoa_small_p8.cu",
-                                       "nmfoa_small_p12.cu", "nmfoa_mid_w8.cu", "nmfoa_mid_w4.cu", "nmfoa_mid_ws.cu", "probes.cu")]
-HDR = [os.path.join(CSRC, f) for f in ("common.cuh", "launch.h", "nmfoa_small.cuh", "nmfoa_mid.cuh")]
+                                       "nmfoa_small_p12.cu", "nmfoa_mid_w8.cu", "nmfoa_mid_w4.cu", "nmfoa_mid_ws.cu", "nmfoa_wide.cu", "probes.cu")]
+HDR = [os.path.join(CSRC, f) for f in ("common.cuh", "launch.h", "tma.cuh", "nmfoa_small.cuh", "nmfoa_mid.cuh")]
 # tuning aid: DEGNORM_B200_VARIANT=name with DEGNORM_B200_NVCC_FLAGS="-DMID_FEAT=3" builds libdegnorm_b200.name.so
 # beside the product library (loaded with DEGNORM_B200_LIB=<path>, see _lib.py)
 VARIANT = os.environ.get("DEGNORM_B200_VARIANT", "")

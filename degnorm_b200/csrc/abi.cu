@@ -227,6 +227,13 @@ int run_kernel(int mode, const double *cov, const int64_t *off, const int32_t *o
         if (plan->threads == 256) return dn_launch_mid8(a, plan, st);
         return dn_launch_midws(a, plan, st);
     }
+    if (plan->tile == 8 && plan->threads == WIDE_THREADS) {
+        // wide path (49..208 samples, baseline selection only)
+        if (mode != MODE_BS || prm->p < WIDE_MIN_P || wide_pp(prm->p) > WIDE_MAX_PP) return fail(DN_ERR_INVALID, "plan does not match params (use dn_make_plan)%s");
+        a.pp = wide_pp(prm->p);
+        a.ws_stride = wide_slab_doubles(a.pp, plan->ws_cols);
+        return dn_launch_wide(a, plan, st);
+    }
     if (plan->tile == 0) {
         // small-p path (baseline selection only)
         const int P = small_P(prm->p);
@@ -303,6 +310,28 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         if (clusters < 1) clusters = 1;
         plan->ctas = (int32_t)(clusters * cl);
         plan->ws_bytes = 256 + (long long)plan->ctas * mid_slab_doubles(share) * 8;
+        return DN_OK;
+    }
+    if (!for_init && cluster >= 0 && prm->p >= WIDE_MIN_P && wide_pp(prm->p) <= WIDE_MAX_PP) {
+        // ---- wide path (49..208 samples): one 8 x 8 Gram tile per thread, streamed; optional cluster per gene
+        int cl = cluster > 1 ? cluster : 1;
+        if (cl != 1 && cl != 2 && cl != 4 && cl != 8 && cl != 16) return fail(DN_ERR_INVALID, "cluster must be 1, 2, 4, 8 or 16%s");
+        const int pp = wide_pp(prm->p);
+        long long share = (max_cols + cl - 1) / cl;
+        share = (share + WIDE_CHUNK - 1) / WIDE_CHUNK * WIDE_CHUNK;
+        plan->tile = 8;
+        plan->threads = WIDE_THREADS;
+        plan->cluster = cl;
+        plan->chunk_cols = WIDE_CHUNK;
+        plan->resident_cols = 0;
+        plan->smem_bytes = (int32_t)(wide_carve(pp).total * 8);
+        if (plan->smem_bytes > max_smem_optin) return fail(DN_ERR_UNSUPPORTED, "shared memory carve-up does not fit%s");
+        plan->ws_cols = share;
+        long long clusters = (long long)sm_count / cl;
+        if (clusters > n_work) clusters = n_work;
+        if (clusters < 1) clusters = 1;
+        plan->ctas = (int32_t)(clusters * cl);
+        plan->ws_bytes = 256 + (long long)plan->ctas * wide_slab_doubles(pp, share) * 8;
         return DN_OK;
     }
     const int P = for_init ? 0 : small_P(prm->p);

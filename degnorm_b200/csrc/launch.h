@@ -116,7 +116,7 @@ __host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols
 // chunk) and 4 warps (two such CTAs per SM, 32-column chunks).
 constexpr int MID_P = 48;             // samples padded to this
 constexpr int MID_WARPS = 8;          // Gram warps per CTA
-constexpr int MID_UPD_WARPS = 2;      // update warps of the warp-specialised instantiation
+constexpr int MID_UPD_WARPS = 4;      // update warps of the warp-specialised instantiation
 constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
 constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
 __host__ __device__ constexpr int mid_chunk(int nw) { return 8 * nw; }   // columns per ring stage
@@ -151,7 +151,45 @@ __host__ __device__ inline long long mid_slab_doubles(long long ws_cols) {
     return (d + 31) / 32 * 32;
 }
 
+// ---- wide kernel (49 <= p <= 208; nmfoa_wide.cu): one 8 x 8 Gram tile per thread, streamed through a TMA ring ---------
+constexpr int WIDE_THREADS = 384;     // 12 warps: three per SM sub-partition
+constexpr int WIDE_CHUNK = 16;        // columns per ring stage
+constexpr int WIDE_RING = 3;
+constexpr int WIDE_MAX_PP = 208;      // 26 x 27 / 2 = 351 tiles <= threads: the triangle of 208 samples fills the register file
+constexpr int WIDE_MIN_P = 49;
+constexpr int WIDE_MAX_KS = 8;        // k-slices of a chunk's columns when there are fewer tiles than threads
+constexpr int WIDE_NSMALL = 11;       // pp-sized shared vectors
+__host__ __device__ inline int wide_pp(int p) { return (p + 7) / 8 * 8; }
+__host__ __device__ inline int wide_tiles(int pp) { return (pp / 8) * (pp / 8 + 1) / 2; }
+__host__ __device__ inline int wide_kslices(int ntiles) {
+    int ks = WIDE_THREADS / ntiles;
+    return ks < 1 ? 1 : (ks > WIDE_MAX_KS ? WIDE_MAX_KS : ks);
+}
+struct WideCarve { long long small, red, binm, alive, ibuf, lw, mbar, part, ring, total; };
+__host__ __device__ inline WideCarve wide_carve(int pp) {
+    WideCarve c;
+    long long o = 0;
+    c.small = o; o += (long long)WIDE_NSMALL * pp;
+    c.red = o;   o += 64;
+    c.binm = o;  o += DN_MAX_BINS;
+    c.alive = o; o += DN_MAX_BINS / 2;
+    c.ibuf = o;  o += 16;
+    c.lw = o;    o += DN_MAX_BINS / 2;
+    c.mbar = o;  o += 4;
+    c.part = o;  o += (long long)wide_tiles(pp) * 16;       // partial products of the register-tile mat-vec
+    c.ring = o;  o += (long long)WIDE_RING * 2 * WIDE_CHUNK * (pp + 2);
+    c.total = o;
+    return c;
+}
+// per-CTA slab (doubles): G + two squaring matrices, two exchange slots, k-slice scratch, x, M, residuals, t
+__host__ __device__ inline long long wide_slab_doubles(int pp, long long ws_cols) {
+    const long long ne = (long long)wide_tiles(pp) * 64;
+    const long long d = 3ll * pp * pp + 2 * ne + (WIDE_MAX_KS - 1) * ne + (2ll * (pp + 2) + 2) * ws_cols;
+    return (d + 31) / 32 * 32;
+}
+
 // launchers (each defined in its own translation unit)
+int dn_launch_wide(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_mid8(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_mid4(const KArgs &a, const dn_plan *plan, cudaStream_t st);
 int dn_launch_midws(const KArgs &a, const dn_plan *plan, cudaStream_t st);

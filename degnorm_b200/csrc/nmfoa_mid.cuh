@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "launch.h"
+#include "tma.cuh"
 namespace cg = cooperative_groups;
 
 namespace {
@@ -54,64 +55,12 @@ constexpr int MNT = (MNW + MNA) * 32;     // threads
 constexpr int MNWT = MNW + MNA;           // warps
 constexpr int MCH = mid_chunk(MNW);       // columns per chunk
 constexpr int MCPR = MNT / 4;             // columns per CTA step where 4 lanes share a column (scan-type passes)
+constexpr int WS_REG_BASE = 168, WS_REG_B = 192, WS_REG_A = 112;   // see gram_mid_ws: 128 (168 - A) >= 256 (B - 168)
 constexpr int IB_WCOUNT = 1;              // ibuf slots: [0] queue ticket, [1 .. 12] per-warp counts, [20] eigen flag,
 constexpr int IB_EIG = 20;                //             [24 .. 26] consumers done with a ring stage
 constexpr int IB_FREE = 24;
 constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
 constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
-
-// ---- TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers --------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                     smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE;\n"
-        "bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// generic-proxy accesses (ordinary loads / stores, already ordered by a barrier) before async-proxy (TMA) accesses
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
-// the same for shared memory only (SASS: FENCE.VIEW.ASYNC.S without the MEMBAR.GPU of the full fence)
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-
-// shared -> global bulk copy (TMA store), tracked by the issuing thread's bulk async-groups
-__device__ __forceinline__ void bulk_s2g(void *gmem_dst, const void *smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-                 "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
-// global load that bypasses L1 (the slab's M is written by the async proxy when MID_TMA_STORE is on: an L1 line
-// cached by an earlier ordinary load would be stale)
-__device__ __forceinline__ void ld12cg(const double *p, double (&x)[12]) {
-    const double2 *q = reinterpret_cast<const double2 *>(p);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) { const double2 t = __ldcg(q + i); x[2 * i] = t.x; x[2 * i + 1] = t.y; }
-}
 
 struct MGene {
     double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *buf, *ring;
@@ -169,7 +118,20 @@ __device__ void mclu_allsum(MGene &g, const double *vals, int n, double *out) {
 }
 
 // ---- end of a pass: the Gram warps' partial sums -> CTA sum -> cluster sum -> square G in shared memory -----------
-__device__ void gram_finish(MGene &g, double (&acc)[6][8]) {
+struct FinArgs {
+    double *buf, *slots, *G;
+    const int *tab;
+    long long slot_stride;
+    int crank, csize, xpar;
+};
+__device__ __forceinline__ FinArgs fin_args(const MGene &g) {
+    FinArgs f;
+    f.buf = g.buf; f.slots = g.slots; f.G = g.G; f.tab = g.tab; f.slot_stride = g.slot_stride;
+    f.crank = g.crank; f.csize = g.csize; f.xpar = g.xpar;
+    return f;
+}
+// (returns the exchange-slot parity to use next)
+__device__ __forceinline__ int gram_finish(FinArgs g, double (&acc)[6][8]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
     double *mine = g.buf + (long long)(warp & 3) * MNE + lane * 48;
@@ -232,6 +194,7 @@ __device__ void gram_finish(MGene &g, double (&acc)[6][8]) {
     }
     if (g.csize > 1) g.xpar ^= 1;
     __syncthreads();
+    return g.xpar;
 }
 
 // ---- one pass over this CTA's columns: (optional multiplier update) + Gram of M -> G (shared, identical cluster-wide)
@@ -392,7 +355,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
 #pragma unroll
         for (int q = 0; q < MID_RING - 1; ++q) issue(q, true);
     }
-    gram_finish(g, acc);
+    g.xpar = gram_finish(fin_args(g), acc);
 }
 
 // ---- the same pass, warp-specialised (MID_NA > 0) ------------------------------------------------------------------
@@ -406,8 +369,26 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
 // so no thread ever waits for a stage to drain, and no block barrier is taken inside a pass: the update of chunk k + 1
 // (latency-bound: shared loads -> dot product -> two shuffles -> 36 FMAs -> stores) overlaps the Gram FMAs of chunk k
 // (throughput-bound on the FP64 pipe and the shared-memory wavefronts) on the same SM sub-partitions.
+// Registers: twelve warps are three per SM sub-partition, whose 16,384 registers give every thread 168.  The pass
+// takes what it needs by value (PassArgs) instead of through the per-gene state, whose three dozen pointers would
+// otherwise stay live across it, and for its duration the update warps (one warpgroup) hand registers to the Gram
+// warps (two warpgroups) with setmaxnreg.  The CTA's register pool is what the launch gave it (384 x 168), so the
+// hand-over has to balance: 128 threads x (168 - WS_REG_A) >= 256 threads x (WS_REG_B - 168) -- a Gram warp that asks
+// for more than the update warps released would wait for ever.  With it ptxas keeps the 48 accumulators and two
+// columns' operands in registers through the column loop (without it the loop spills).
+struct PassArgs {
+    double *ring, *M, *X, *v;
+    unsigned long long *mbar;
+    int *ibuf;
+    FinArgs fin;
+    double c;
+    int n_cur;
+    unsigned seq;
+    int primed;
+};
+struct PassOut { unsigned seq; int xpar; };
 template <bool UPDATE>
-__device__ void gram_mid_ws(const KArgs &a, MGene &g, bool prime_next) {
+__device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prime_next) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = g.n_cur;
     const int nchunk = (n + MCH - 1) / MCH;
@@ -455,8 +436,9 @@ __device__ void gram_mid_ws(const KArgs &a, MGene &g, bool prime_next) {
 
     if (is_b) {
         // -------------------------------------------------------------------------------------------- Gram warps
-        const int tr0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane) : -1;
-        const int tc0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane + 1) : 0;
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_REG_B));
+        const int tr0 = lane < MNTILE ? g.fin.tab[2 * lane] : -1;
+        const int tc0 = lane < MNTILE ? g.fin.tab[2 * lane + 1] : 0;
         const int rot = tc0 >> 4;
         const int uo0 = tc0 + 2 * ((0 + rot) & 3), uo1 = tc0 + 2 * ((1 + rot) & 3), uo2 = tc0 + 2 * ((2 + rot) & 3),
                   uo3 = tc0 + 2 * ((3 + rot) & 3);
@@ -505,12 +487,16 @@ __device__ void gram_mid_ws(const KArgs &a, MGene &g, bool prime_next) {
             __syncwarp();
             if (lane == 0) release(ch);
         }
+        // (the warps of a warpgroup synchronise between two setmaxnreg instructions, as PTX requires)
+        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + (warp >> 2)) : "memory");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_REG_BASE));
     } else {
         // -------------------------------------------------------------------------------------------- update warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_REG_A));
         const int aw = warp - MNW;                            // this warp's columns of a chunk: [CPA aw, CPA (aw + 1))
         constexpr int CPA = MCH / (MNA > 0 ? MNA : 1);
         const int q4 = lane & 3;
-        const double c = a.c;
+        const double c = g.c;
         double vq[12];
         if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
 #pragma unroll 1
@@ -570,16 +556,19 @@ __device__ void gram_mid_ws(const KArgs &a, MGene &g, bool prime_next) {
         if constexpr (UPDATE) {
             if (lane == 0) bulk_wait_all();                   // the slab holds this warp's columns of the new M
         }
+        __syncwarp();
+        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + (warp >> 2)) : "memory");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_REG_BASE));
     }
-    g.seq = seq0 + (unsigned)nchunk;
+    PassOut out;
+    out.seq = seq0 + (unsigned)nchunk;
     fence_proxy_async();
     __syncthreads();
-    g.primed = prime_next;
     if (prime_next && tid == 0) {
         // the next pass is an update pass over the same columns: request its first chunks now (they travel while the
         // partial Grams are reduced and the eigen-solve runs)
         for (int q = 0; q < MID_RING && q < nchunk; ++q) {
-            const unsigned st = (g.seq + (unsigned)q) % MID_RING;
+            const unsigned st = (out.seq + (unsigned)q) % MID_RING;
             double *dst = g.ring + st * STG;
             fence_proxy_async_smem();
             mbar_expect_tx(full + st, 2 * CHB);
@@ -587,7 +576,8 @@ __device__ void gram_mid_ws(const KArgs &a, MGene &g, bool prime_next) {
             bulk_g2s(dst + MCH * MCS, g.X + (long long)q * (MCH * MCS), CHB, full + st);
         }
     }
-    gram_finish(g, acc);
+    out.xpar = gram_finish(g.fin, acc);
+    return out;
 }
 
 // ---- top eigenvector of G (MP x MP, shared); same rules as eig_warp in nmfoa_tiled.cu -----------------------------
@@ -788,11 +778,19 @@ __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res,
     const int T = a.nmf_iter;
     g.primed = false;
     if constexpr (MNA > 0) {
-        gram_mid_ws<false>(a, g, T > 0);
-        eig_mid(a, g, true);
-        for (int it = 0; it < T; ++it) {
-            gram_mid_ws<true>(a, g, it + 1 < T);
-            eig_mid(a, g, false);
+        PassArgs pa;
+        pa.ring = g.ring; pa.M = g.M; pa.X = g.X; pa.v = g.v; pa.mbar = g.mbar; pa.ibuf = g.ibuf;
+        pa.c = a.c; pa.n_cur = g.n_cur;
+        for (int it = -1; it < T; ++it) {
+            pa.fin = fin_args(g);
+            pa.seq = g.seq;
+            pa.primed = g.primed ? 1 : 0;
+            const bool prime_next = it + 1 < T;
+            const PassOut po = it < 0 ? gram_mid_ws<false>(pa, prime_next) : gram_mid_ws<true>(pa, prime_next);
+            g.seq = po.seq;
+            g.xpar = po.xpar;
+            g.primed = prime_next;
+            eig_mid(a, g, it < 0);
         }
     } else {
         gram_mid<false>(a, g, T > 0);
@@ -805,11 +803,8 @@ __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res,
     final_pass_mid(a, g, first, want_res, e_first_g);
 }
 
-#if MID_NA > 0
-__global__ void __maxnreg__(200) nmfoa_mid_kernel(const KArgs a) {      // 320 threads x 200 registers: one CTA per SM
-#else
+// (warp-specialised instantiation: 12 warps = three per SM sub-partition, whose 16,384 registers allow 168 per thread)
 __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const KArgs a) {
-#endif
     extern __shared__ double smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int p = a.p;

@@ -20,6 +20,10 @@ RESIDENT_TIERS = (128, 256, 512, 1024, 2048, 4096, 8192, 16384)
 # mid-p kernel (13 <= p <= 48): (cluster size, up to this many candidate columns)
 MID_MAX_P = 48
 MID_CLUSTERS = ((1, 16384), (2, 32768), (4, 65536), (8, 131072), (16, 1 << 31))   # measured sweep: profiles/r01_mid_cluster_sweep.txt
+# wide kernel (49 <= p <= 208): one 8 x 8 Gram tile per thread; a CTA needs ~400 clocks per column-pass at p = 200, so
+# genes get a cluster earlier than on the mid-p path
+WIDE_MIN_P, WIDE_MAX_P = 49, 208
+WIDE_CLUSTERS = ((1, 8192), (2, 16384), (4, 32768), (8, 65536), (16, 1 << 31))
 # small-p kernel (p <= 12): (columns, warps per CTA); the column caps make whole numbers of CTAs fill an SM's 227 KB
 SMALL_TIERS = ((36, 1), (64, 1), (96, 1), (154, 2), (204, 2), (284, 2), (420, 4), (856, 8))
 
@@ -89,6 +93,8 @@ class ShardEngine(object):
         self.use_clusters = True
         self.cluster_min_cols = -1        # -1: default (4096 columns at P = 12); 0: clusters right above the tiers
         self.use_mid = True
+        self.use_wide = True
+        self.wide_clusters = None
         self.mid_clusters = None
         self.mid_warps = 0                # 0: 8 warps, one CTA per SM; 4: two 4-warp CTAs per SM
         self.force_cluster = 0
@@ -184,8 +190,9 @@ class ShardEngine(object):
         cand = (L + r - 1) // r
         if self.force_streamed or self.force_cluster:
             # testing aids: everything through the streamed tier and / or through clusters of a given size
-            cl = self.force_cluster if self.p <= MID_MAX_P else 0
-            if 12 < self.p <= MID_MAX_P and not self.use_mid:
+            wide = WIDE_MIN_P <= self.p <= WIDE_MAX_P
+            cl = self.force_cluster if (self.p <= MID_MAX_P or wide) else 0
+            if (12 < self.p <= MID_MAX_P and not self.use_mid) or (wide and not self.use_wide):
                 cl = -1
             self.buckets.append(self._bucket(np.arange(n), cand, 0 if self.force_streamed else -1,
                                              warps=self.mid_warps if 12 < self.p <= MID_MAX_P else 0, cluster=cl))
@@ -243,7 +250,15 @@ class ShardEngine(object):
                     self.buckets.append(self._bucket(sel, cand, 0, warps=self.mid_warps, cluster=cl))
                     left[sel] = False
             return
-        tiled = -1 if self.p <= MID_MAX_P else 0          # (13..48 samples: ask the planner for the tiled kernel)
+        if WIDE_MIN_P <= self.p <= WIDE_MAX_P and self.use_wide:
+            # wide kernel (49..208 samples): every gene streams from its slab; cluster size follows gene length
+            for cl, cap in (self.wide_clusters or WIDE_CLUSTERS):
+                sel = np.flatnonzero(left & (cand <= cap))
+                if len(sel):
+                    self.buckets.append(self._bucket(sel, cand, 0, cluster=cl))
+                    left[sel] = False
+            return
+        tiled = -1 if self.p <= WIDE_MAX_P else 0         # (13..208 samples: ask the planner for the tiled kernel)
         for tier in RESIDENT_TIERS:
             plan = self._make_plan(tier, 1, tier, cluster=tiled)
             if plan.resident_cols < tier:

@@ -288,7 +288,7 @@ def test_cluster_path_equals_single_cta_path(p, cluster, streamed):
                                              (48, 1, 8), (30, 16, 8), (48, 1, 4), (17, 2, 4), (30, 16, 4)])
 def test_mid_kernel_equals_tiled_kernel(p, cluster, warps):
     """13..48 samples: the streamed mid-p kernel (warps = 0: the default warp-specialised instantiation, 8 Gram warps
-    + 2 update warps; 8: every warp updates and accumulates; 4: two 4-warp CTAs per SM; optionally one cluster per
+    + 4 update warps; 8: every warp updates and accumulates; 4: two 4-warp CTAs per SM; optionally one cluster per
     gene) against the generic tiled kernel on the same genes: identical decisions and call sequences, DI equal to
     rounding."""
     import torch
@@ -307,7 +307,38 @@ def test_mid_kernel_equals_tiled_kernel(p, cluster, warps):
         eng.force_cluster = cluster if (use_mid and cluster > 1) else 0
         eng.load(flat.cuda(), off, torch.from_numpy(reads).cuda())
         assert all((int(b.plan.tile) == 6) == use_mid for b in eng.buckets)
-        assert not use_mid or all(int(b.plan.threads) == (320 if warps == 0 else 32 * warps) for b in eng.buckets)
+        assert not use_mid or all(int(b.plan.threads) == (384 if warps == 0 else 32 * warps) for b in eng.buckets)
+        o = eng.run(None, want_estimates=True)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu().numpy() for k, v in o.items() if torch.is_tensor(v)})
+    a, b = outs
+    np.testing.assert_array_equal(a["ran"], b["ran"])
+    np.testing.assert_array_equal(a["counters"][:, :, :4], b["counters"][:, :, :4])
+    np.testing.assert_array_equal(a["counters"][:, :, 5:7], b["counters"][:, :, 5:7])
+    np.testing.assert_allclose(a["rho"], b["rho"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(a["est"], b["est"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("p,cluster", [(49, 1), (64, 1), (100, 1), (200, 1), (208, 1), (200, 2), (130, 4), (72, 16)])
+def test_wide_kernel_equals_tiled_kernel(p, cluster):
+    """49..208 samples: the wide kernel (one 8 x 8 Gram tile per thread held in registers for a whole pass, TMA ring,
+    register-tile eigen mat-vec; k-slices for narrow cohorts; optionally one cluster per gene) against the generic
+    tiled kernel on the same genes: identical decisions and call sequences, DI equal to rounding."""
+    import torch
+    from degnorm_b200.engine import Params, ShardEngine
+    from degnorm_b200.packing import pack_coverage
+    from degnorm_b200.synth import synth_numpy
+    lengths = np.array([300, 520, 1210, 150, 95, 33])
+    mats, reads = synth_numpy(len(lengths), p, 500 + p, lengths=lengths, jitter=1e-6)
+    prm = Params(degnorm_iter=2, nmf_iter=12)
+    flat, off = pack_coverage(mats, p)
+    outs = []
+    for use_wide in (False, True):
+        eng = ShardEngine(prm, p, "cuda:0")
+        eng.use_wide = use_wide
+        eng.force_cluster = cluster if (use_wide and cluster > 1) else 0
+        eng.load(flat.cuda(), off, torch.from_numpy(reads).cuda())
+        assert all((int(b.plan.threads) == 384) == use_wide for b in eng.buckets)
         o = eng.run(None, want_estimates=True)
         torch.cuda.synchronize()
         outs.append({k: v.cpu().numpy() for k, v in o.items() if torch.is_tensor(v)})

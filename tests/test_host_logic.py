@@ -94,14 +94,24 @@ def test_plan_is_pure_host_arithmetic():
     assert plan.ws_cols % 64 == 0 and plan.ctas % 16 == 0 and plan.smem_bytes <= 232448
     assert lib.dn_make_plan(C.byref(prm48), 100000, 1000, -1, 0, 0, -1, 148, 232448, C.byref(plan)) == 0
     assert plan.tile == 4 and 0 < plan.resident_cols < 100000 and plan.ws_cols >= 100000
+    # 49..208 samples: the wide kernel (one 8 x 8 Gram tile per thread, 384 threads, 16-column chunks); cluster = -1
+    # asks for the generic tiled kernel, which also takes 209..256 samples
     prm64 = Params().to_c(64)
-    assert lib.dn_make_plan(C.byref(prm64), 5000, 1000, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0 and plan.tile == 4
+    assert lib.dn_make_plan(C.byref(prm64), 5000, 1000, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert (plan.tile, plan.threads, plan.chunk_cols, plan.ctas) == (8, 384, 16, 148) and plan.ws_cols == 5008
+    assert lib.dn_make_plan(C.byref(prm64), 5000, 1000, 0, 0, 0, -1, 148, 232448, C.byref(plan)) == 0 and plan.tile == 4
     bad = Params().to_c(1)
     assert lib.dn_make_plan(C.byref(bad), 128, 10, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_INVALID
     assert b"2 samples" in lib.dn_last_error()
     p200 = Params().to_c(200)
-    assert lib.dn_make_plan(C.byref(p200), 3000, 100, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
-    assert plan.tile == 8 and plan.resident_cols == 0 and plan.ws_bytes > 0
+    assert lib.dn_make_plan(C.byref(p200), 3000, 100, 0, 0, 0, 4, 148, 232448, C.byref(plan)) == 0
+    assert (plan.tile, plan.threads, plan.cluster, plan.ctas) == (8, 384, 4, 148) and plan.ws_cols == 752
+    assert plan.resident_cols == 0 and plan.ws_bytes > 0 and plan.smem_bytes <= 232448
+    p208, p209 = Params().to_c(208), Params().to_c(209)
+    assert lib.dn_make_plan(C.byref(p208), 3000, 100, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert plan.threads == 384 and plan.smem_bytes <= 232448
+    assert lib.dn_make_plan(C.byref(p209), 3000, 100, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == 0
+    assert (plan.tile, plan.threads) == (8, 256)
     big = Params().to_c(5000)
     assert lib.dn_make_plan(C.byref(big), 128, 10, 0, 0, 0, 0, 148, 232448, C.byref(plan)) == _lib.DN_ERR_UNSUPPORTED
 
@@ -290,7 +300,7 @@ def test_device_coverage_handle_filters_like_filter_genes_on_host_tensors():
 
 def test_mid_kernel_plans_are_pure_host_arithmetic():
     """dn_make_plan for 13..48 samples (no device call): the default warp-specialised instantiation (8 Gram warps +
-    2 update warps) and the 8-warp one take one CTA per SM with a 3 x 51.2 KB ring, the 4-warp one fits two CTAs per
+    4 update warps) and the 8-warp one take one CTA per SM with a 3 x 51.2 KB ring, the 4-warp one fits two CTAs per
     SM (G parked in the free ring stage); workspace columns are whole chunks; clusters divide the CTA count."""
     import ctypes as C
     from degnorm_b200 import _lib
@@ -305,7 +315,7 @@ def test_mid_kernel_plans_are_pure_host_arithmetic():
         assert rc == 0, lib.dn_last_error()
         return pl
     pw = plan(5000, 10000, 0, 1)
-    assert (pw.tile, pw.threads, pw.cluster, pw.ctas) == (6, 320, 1, 148)
+    assert (pw.tile, pw.threads, pw.cluster, pw.ctas) == (6, 384, 1, 148)
     p8 = plan(5000, 10000, 8, 1)
     assert (p8.tile, p8.threads, p8.cluster, p8.ctas) == (6, 256, 1, 148)
     assert (pw.smem_bytes, pw.ws_cols, pw.ws_bytes) == (p8.smem_bytes, p8.ws_cols, p8.ws_bytes)
