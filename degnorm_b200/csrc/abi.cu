@@ -296,7 +296,7 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         // anything else (default): the warp-specialised instantiation, 8 Gram warps + 4 update warps
         const int nw = warps == 4 ? 4 : MID_WARPS;
         const int na = (warps == 4 || warps == 8) ? 0 : MID_UPD_WARPS;
-        const int chunk = mid_chunk(nw);
+        const int chunk = na > 0 ? MID_WS_CHUNK : mid_chunk(nw);
         long long share = (max_cols + cl - 1) / cl;
         share = (share + chunk - 1) / chunk * chunk;
         plan->tile = 6;

@@ -118,6 +118,8 @@ constexpr int MID_P = 48;             // samples padded to this
 constexpr int MID_WARPS = 8;          // Gram warps per CTA
 constexpr int MID_UPD_WARPS = 4;      // update warps of the warp-specialised instantiation
 constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
+constexpr int MID_WS_CHUNK = 32;      // warp-specialised instantiation: columns per ring stage ...
+constexpr int MID_WS_RING = 6;        // ... and stages (same bytes as 3 stages of 64 columns)
 constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
 __host__ __device__ constexpr int mid_chunk(int nw) { return 8 * nw; }   // columns per ring stage
 
@@ -133,7 +135,7 @@ __host__ __device__ inline MidCarve mid_carve(int nw) {
     c.ibuf = o;  o += 16;
     c.lw = o;    o += DN_MAX_BINS / 2;
     c.tab = o;   o += 32;
-    c.mbar = o;  o += 8;                        // MID_RING "chunk landed" + MID_RING "chunk updated" mbarriers
+    c.mbar = o;  o += 16;                       // "chunk landed" + "chunk updated" mbarriers (up to 6 + 6)
     const long long stage = 2ll * mid_chunk(nw) * (MID_P + 2);
     // 4-warp CTAs (two per SM): G lives in the ring's last stage, which is free between two passes (the ring is
     // primed with chunks 0 and 1 only) -- the eigen-solve is the only user of G
@@ -161,8 +163,14 @@ constexpr int WIDE_MAX_KS = 8;        // k-slices of a chunk's columns when ther
 constexpr int WIDE_NSMALL = 11;       // pp-sized shared vectors
 __host__ __device__ inline int wide_pp(int p) { return (p + 7) / 8 * 8; }
 __host__ __device__ inline int wide_tiles(int pp) { return (pp / 8) * (pp / 8 + 1) / 2; }
-__host__ __device__ inline int wide_kslices(int ntiles) {
-    int ks = WIDE_THREADS / ntiles;
+// lane slots of one k-slice: the tiles row-major, every tile row padded to an even length (nmfoa_wide.cu)
+__host__ __device__ inline int wide_slots(int nb) {
+    int s = 0;
+    for (int ti = 0; ti < nb; ++ti) s += (nb - ti) + ((nb - ti) & 1);
+    return s;
+}
+__host__ __device__ inline int wide_kslices(int nb) {
+    int ks = WIDE_THREADS / wide_slots(nb);
     return ks < 1 ? 1 : (ks > WIDE_MAX_KS ? WIDE_MAX_KS : ks);
 }
 struct WideCarve { long long small, red, binm, alive, ibuf, lw, mbar, part, ring, total; };

@@ -53,11 +53,19 @@ constexpr int MP = MID_P;                 // padded samples
 constexpr int MCS = MID_P + 2;            // column stride (doubles)
 constexpr int MNT = (MNW + MNA) * 32;     // threads
 constexpr int MNWT = MNW + MNA;           // warps
-constexpr int MCH = mid_chunk(MNW);       // columns per chunk
+// Warp-specialised instantiation: 32-column chunks in a 6-stage ring (the same shared memory as 3 stages of 64): the
+// stage of chunk k is refilled with chunk k + 6 once its consumers are done, so FOUR chunks (100 KB) are in flight per
+// SM instead of one.  With one 51 KB chunk in flight per SM the pass was bound by memory-level parallelism (one chunk per
+// HBM round trip), whatever the roles did.
+constexpr int MCH = MNA > 0 ? MID_WS_CHUNK : mid_chunk(MNW);     // columns per chunk
+constexpr int MRING = MNA > 0 ? MID_WS_RING : MID_RING;          // ring stages
 constexpr int MCPR = MNT / 4;             // columns per CTA step where 4 lanes share a column (scan-type passes)
-constexpr int WS_REG_BASE = 168, WS_REG_B = 192, WS_REG_A = 112;   // see gram_mid_ws: 128 (168 - A) >= 256 (B - 168)
+#ifndef WS_SETMAXNREG
+#define WS_SETMAXNREG 2
+#endif
+constexpr int WS_REG_BASE = 168, WS_REG_B = 184, WS_REG_A = 136;   // see gram_mid_ws: 128 (168 - A) >= 256 (B - 168)
 constexpr int IB_WCOUNT = 1;              // ibuf slots: [0] queue ticket, [1 .. 12] per-warp counts, [20] eigen flag,
-constexpr int IB_EIG = 20;                //             [24 .. 26] consumers done with a ring stage
+constexpr int IB_EIG = 20;                //             [24 .. 29] consumers done with a ring stage
 constexpr int IB_FREE = 24;
 constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
 constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
@@ -394,7 +402,7 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
     const int nchunk = (n + MCH - 1) / MCH;
     constexpr int STG = 2 * MCH * MCS;                     // doubles per ring stage (M then x)
     constexpr unsigned CHB = MCH * MCS * 8;                // bytes of one array's chunk
-    unsigned long long *full = g.mbar, *upd = g.mbar + MID_RING;
+    unsigned long long *full = g.mbar, *upd = g.mbar + MRING;
     volatile int *freec = g.ibuf + IB_FREE;
     const bool is_b = warp < MNW;
     // Ring bookkeeping: chunks are numbered through the whole kernel (g.seq = chunks consumed so far, the same in
@@ -404,7 +412,7 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
 
     // request chunk ch of this pass (caller: the stage is free, the slab holds the data)
     auto issue = [&](int ch, bool with_x) {
-        const unsigned st = (seq0 + (unsigned)ch) % MID_RING;
+        const unsigned st = (seq0 + (unsigned)ch) % MRING;
         double *dst = g.ring + st * STG;
         fence_proxy_async_smem();
         mbar_expect_tx(full + st, with_x ? 2 * CHB : CHB);
@@ -413,20 +421,20 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
     };
     // one consumer (a B warp, or an A warp whose bulk store has read the stage) is done with chunk ch; called by lane 0
     auto release = [&](int ch) {
-        if (ch + MID_RING < nchunk) {
-            const unsigned st = (seq0 + (unsigned)ch) % MID_RING;
+        if (ch + MRING < nchunk) {
+            const unsigned st = (seq0 + (unsigned)ch) % MRING;
             __threadfence_block();
             const int old = atomicAdd(const_cast<int *>(freec + st), 1);
             if (old == MNW + MNA - 1) {
                 freec[st] = 0;
                 __threadfence_block();
-                issue(ch + MID_RING, UPDATE);
+                issue(ch + MRING, UPDATE);
             }
         }
     };
     if (!g.primed) {
         if (tid == 0)
-            for (int q = 0; q < MID_RING && q < nchunk; ++q) issue(q, UPDATE);
+            for (int q = 0; q < MRING && q < nchunk; ++q) issue(q, UPDATE);
     }
     double acc[6][8];
 #pragma unroll
@@ -436,7 +444,9 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
 
     if (is_b) {
         // -------------------------------------------------------------------------------------------- Gram warps
+#if WS_SETMAXNREG >= 2
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_REG_B));
+#endif
         const int tr0 = lane < MNTILE ? g.fin.tab[2 * lane] : -1;
         const int tc0 = lane < MNTILE ? g.fin.tab[2 * lane + 1] : 0;
         const int rot = tc0 >> 4;
@@ -444,8 +454,8 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
                   uo3 = tc0 + 2 * ((3 + rot) & 3);
 #pragma unroll 1
         for (int ch = 0; ch < nchunk; ++ch) {
-            const unsigned k = seq0 + (unsigned)ch, st = k % MID_RING;
-            mbar_wait(upd + st, (k / MID_RING) & 1u);
+            const unsigned k = seq0 + (unsigned)ch, st = k % MRING;
+            mbar_wait(upd + st, (k / MRING) & 1u);
             const double *sM = g.ring + st * STG;
             const int ncol = min(MCH, n - ch * MCH);
             if (tr0 >= 0) {
@@ -487,12 +497,17 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
             __syncwarp();
             if (lane == 0) release(ch);
         }
+#if WS_SETMAXNREG >= 2
         // (the warps of a warpgroup synchronise between two setmaxnreg instructions, as PTX requires)
         asm volatile("bar.sync %0, 128;\n" ::"r"(1 + (warp >> 2)) : "memory");
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_REG_BASE));
+        asm volatile("bar.sync 4, %0;\n" ::"n"(MNT) : "memory");      // "surplus returned": see the update warps
+#endif
     } else {
         // -------------------------------------------------------------------------------------------- update warps
+#if WS_SETMAXNREG >= 2
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(WS_REG_A));
+#endif
         const int aw = warp - MNW;                            // this warp's columns of a chunk: [CPA aw, CPA (aw + 1))
         constexpr int CPA = MCH / (MNA > 0 ? MNA : 1);
         const int q4 = lane & 3;
@@ -501,8 +516,8 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
         if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
 #pragma unroll 1
         for (int ch = 0; ch < nchunk; ++ch) {
-            const unsigned k = seq0 + (unsigned)ch, st = k % MID_RING;
-            mbar_wait(full + st, (k / MID_RING) & 1u);
+            const unsigned k = seq0 + (unsigned)ch, st = k % MRING;
+            mbar_wait(full + st, (k / MRING) & 1u);
             double *sM = g.ring + st * STG;
             const int ncol = min(MCH, n - ch * MCH);
             if constexpr (UPDATE) {
@@ -557,18 +572,24 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
             if (lane == 0) bulk_wait_all();                   // the slab holds this warp's columns of the new M
         }
         __syncwarp();
-        asm volatile("bar.sync %0, 128;\n" ::"r"(1 + (warp >> 2)) : "memory");
+#if WS_SETMAXNREG >= 2
+        // The update warps take their registers back only after every Gram warp has returned its surplus (named
+        // barrier 4, all threads).  Re-acquiring at the end of their own loop deadlocks on short passes: an update
+        // warp that is done before the second Gram warpgroup has even asked takes the registers that group waits for.
+        asm volatile("bar.sync 4, %0;\n" ::"n"(MNT) : "memory");
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_REG_BASE));
+#endif
     }
     PassOut out;
-    out.seq = seq0 + (unsigned)nchunk;
+    out.seq = (seq0 + (unsigned)nchunk) % (2 * MRING);     // (stage, parity) of chunk k depend on k mod 2 RING only
     fence_proxy_async();
     __syncthreads();
+
     if (prime_next && tid == 0) {
         // the next pass is an update pass over the same columns: request its first chunks now (they travel while the
         // partial Grams are reduced and the eigen-solve runs)
-        for (int q = 0; q < MID_RING && q < nchunk; ++q) {
-            const unsigned st = (out.seq + (unsigned)q) % MID_RING;
+        for (int q = 0; q < MRING && q < nchunk; ++q) {
+            const unsigned st = (out.seq + (unsigned)q) % MRING;
             double *dst = g.ring + st * STG;
             fence_proxy_async_smem();
             mbar_expect_tx(full + st, 2 * CHB);
@@ -826,10 +847,10 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
     g.use0 = g.use1 = g.use2 = 0;
     g.seq = 0;
     if (tid == 0) {
-        for (int q = 0; q < MID_RING; ++q) mbar_init(g.mbar + q, 1);
+        for (int q = 0; q < MRING; ++q) mbar_init(g.mbar + q, 1);
         // warp-specialised instantiation: "updated" barriers (every update thread arrives) and the consumer counters
-        for (int q = 0; q < MID_RING; ++q) mbar_init(g.mbar + MID_RING + q, MNA > 0 ? MNA * 32 : 1);
-        for (int q = 0; q < MID_RING; ++q) g.ibuf[IB_FREE + q] = 0;
+        for (int q = 0; q < MRING; ++q) mbar_init(g.mbar + MRING + q, MNA > 0 ? MNA * 32 : 1);
+        for (int q = 0; q < MRING; ++q) g.ibuf[IB_FREE + q] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
     cg::cluster_group cl = cg::this_cluster();

@@ -15,8 +15,12 @@
 //     store per chunk.  Phase A (multiplier update: 16 lanes per column) is ~4 % of the work and simply precedes
 //     phase B inside a chunk (two block barriers per chunk of 16 x 20,100 FMAs).
 //   * phase B: per column a thread reads its 8 row operands and 8 column operands from the stage (8 LDS.128) and
-//     issues 64 DFMA.  The column-operand pairs are fetched in an order rotated by (tile column / 2): the lanes of a
-//     quarter-warp then hit distinct banks (the tile columns are 64 bytes apart).
+//     issues 64 DFMA.  Shared memory is as loaded as the FP64 pipe here (4 wavefronts per 128-bit load of 32 distinct
+//     addresses), so the tiles are dealt to the lanes row-major with every tile row padded to an even length: the two
+//     lanes of an aligned pair then share their row operands, and a half-warp whose pairs read the same 16 bytes is
+//     served in ONE wavefront (measured: tools/probe_peaks.py) -- 24 instead of 32 wavefronts per warp and column.
+//     Row- and column-operand pairs are fetched in an order rotated by (tile row / 2) resp. (tile column / 2): the
+//     lanes of a quarter-warp then hit distinct banks (tile rows / columns are 64 bytes apart).
 //   * the p x p eigen-solve never materialises G: every thread multiplies its register tile (and its transpose) with
 //     the current vector, partial products meet in shared memory in a fixed order.  G is written out (to the slab)
 //     only for the rare small-gap fallback (repeated squaring, common.cuh).
@@ -85,7 +89,8 @@ __device__ void wclu_allsum(WGene &g, const double *vals, int n, double *out) {
 }
 
 // ---- one pass over this CTA's columns: (optional multiplier update) + Gram tile of M in `acc` ----------------------
-// acc[r][q] = G[8 ti + r][8 tj + 2 ((q/2 + rot) & 3) + (q & 1)], rot = (tj / 2) & 3 (the rotated fetch order).
+// acc[r][q] = G[8 ti + rot8(r, ti)][8 tj + rot8(q, tj)] (the rotated fetch orders).
+__device__ __forceinline__ int rot8(int q, int t) { return 2 * (((q >> 1) + ((t >> 1) & 3)) & 3) + (q & 1); }
 struct WPass {
     double *ring, *M, *X, *v, *slots, *kslab;
     unsigned long long *mbar;
@@ -124,10 +129,10 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
         issue(1, UPDATE);
     }
     const bool has_tile = g.tile >= 0;
-    const int aoff = 8 * g.ti;
-    const int rot = (g.tj >> 1) & 3;
-    const int uo0 = 8 * g.tj + 2 * ((0 + rot) & 3), uo1 = 8 * g.tj + 2 * ((1 + rot) & 3),
-              uo2 = 8 * g.tj + 2 * ((2 + rot) & 3), uo3 = 8 * g.tj + 2 * ((3 + rot) & 3);
+    const int ao0 = 8 * g.ti + rot8(0, g.ti), ao1 = 8 * g.ti + rot8(2, g.ti), ao2 = 8 * g.ti + rot8(4, g.ti),
+              ao3 = 8 * g.ti + rot8(6, g.ti);
+    const int uo0 = 8 * g.tj + rot8(0, g.tj), uo1 = 8 * g.tj + rot8(2, g.tj), uo2 = 8 * g.tj + rot8(4, g.tj),
+              uo3 = 8 * g.tj + rot8(6, g.tj);
     const int half = tid / WLPC, hl = tid % WLPC;           // phase A: column of the chunk / lane within the column
 #pragma unroll 1
     for (int ch = 0; ch < nchunk; ++ch) {
@@ -158,11 +163,22 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
                 double *mc = sM + half * CS;
                 const double *xc = sM + WCH * CS + half * CS;
                 double tp = 0.0;
-                if (act)
-                    for (int r = hl; r < g.pp; r += WLPC) tp = fma(g.v[r], mc[r], tp);
+                if (act) {
+                    double t0 = 0.0, t1 = 0.0;                      // (two chains, four rows in flight)
+                    int r = hl;
+#pragma unroll 1
+                    for (; r + 3 * WLPC < g.pp; r += 4 * WLPC) {
+                        const double m0 = mc[r], m1 = mc[r + WLPC], m2 = mc[r + 2 * WLPC], m3 = mc[r + 3 * WLPC];
+                        const double v0 = g.v[r], v1 = g.v[r + WLPC], v2 = g.v[r + 2 * WLPC], v3 = g.v[r + 3 * WLPC];
+                        t0 = fma(v0, m0, t0); t1 = fma(v1, m1, t1); t0 = fma(v2, m2, t0); t1 = fma(v3, m3, t1);
+                    }
+                    for (; r < g.pp; r += WLPC) t0 = fma(g.v[r], mc[r], t0);
+                    tp = t0 + t1;
+                }
 #pragma unroll
                 for (int o = 1; o < WLPC; o <<= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
                 if (act) {
+#pragma unroll 4
                     for (int r = hl; r < g.pp; r += WLPC) {
                         const double x = xc[r], m = mc[r];
                         const double res = fma(g.v[r], tp, -x);
@@ -179,10 +195,10 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
 #pragma unroll 1
             for (int cc = g.ks; cc < ncol; cc += g.nks) {
                 const double *mc = sM + cc * CS;
-                const double2 a0 = *reinterpret_cast<const double2 *>(mc + aoff);
-                const double2 a1 = *reinterpret_cast<const double2 *>(mc + aoff + 2);
-                const double2 a2 = *reinterpret_cast<const double2 *>(mc + aoff + 4);
-                const double2 a3 = *reinterpret_cast<const double2 *>(mc + aoff + 6);
+                const double2 a0 = *reinterpret_cast<const double2 *>(mc + ao0);
+                const double2 a1 = *reinterpret_cast<const double2 *>(mc + ao1);
+                const double2 a2 = *reinterpret_cast<const double2 *>(mc + ao2);
+                const double2 a3 = *reinterpret_cast<const double2 *>(mc + ao3);
                 const double ar[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
                 {
                     const double2 u = *reinterpret_cast<const double2 *>(mc + uo0);
@@ -208,12 +224,12 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
         }
     }
     WPassOut out;
-    out.seq = seq0 + (unsigned)nchunk;
+    out.seq = (seq0 + (unsigned)nchunk) % (2 * WIDE_RING);    // (stage, parity) of chunk k depend on k mod 2 RING only
     fence_proxy_async();
     __syncthreads();
     if constexpr (UPDATE) {
-        if (tid == 0) {
-            const unsigned sp = (out.seq - 1) % WIDE_RING;
+        if (tid == 0 && nchunk > 0) {
+            const unsigned sp = (seq0 + (unsigned)nchunk - 1u) % WIDE_RING;
             const int ncp = n - (nchunk - 1) * WCH;
             bulk_s2g(g.M + (long long)(nchunk - 1) * (WCH * CS), g.ring + sp * STG, (unsigned)(ncp * CS * 8));
             bulk_wait_all();                               // the slab holds the whole new M before anyone reads it
@@ -292,12 +308,11 @@ struct WTile { int tile, ti, tj, ks; bool owner; };          // owner: this thre
 
 __device__ __forceinline__ void tile_matvec(const WGene &g, const WTile &t, const double (&acc)[8][8]) {
     if (t.owner) {
-        const int rot = (t.tj >> 1) & 3;
         double vj[8], vi[8], y[8], z[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            vj[q] = g.v[8 * t.tj + 2 * (((q >> 1) + rot) & 3) + (q & 1)];
-            vi[q] = g.v[8 * t.ti + q];
+            vj[q] = g.v[8 * t.tj + rot8(q, t.tj)];
+            vi[q] = g.v[8 * t.ti + rot8(q, t.ti)];
             y[q] = 0.0;
             z[q] = 0.0;
         }
@@ -310,9 +325,9 @@ __device__ __forceinline__ void tile_matvec(const WGene &g, const WTile &t, cons
             }
         double *p0 = g.part + (long long)t.tile * 16;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) p0[r] = y[r];
+        for (int r = 0; r < 8; ++r) p0[rot8(r, t.ti)] = y[r];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) p0[8 + 2 * (((q >> 1) + rot) & 3) + (q & 1)] = (t.ti == t.tj) ? 0.0 : z[q];
+        for (int q = 0; q < 8; ++q) p0[8 + rot8(q, t.tj)] = (t.ti == t.tj) ? 0.0 : z[q];
     }
 }
 // row i of G v: the partial products of the tiles of block row / block column i / 8, in a fixed order
@@ -331,16 +346,9 @@ __device__ void eig_wide(const KArgs &a, WGene &g, const WTile &t, const double 
     const int tid = threadIdx.x;
     const int p = a.p, pp = g.pp;
     if (t.owner && t.ti == t.tj) {
-        const int rot = (t.tj >> 1) & 3;
+        // (rows and columns of a diagonal tile are rotated alike: acc[r][r] is a diagonal entry of G)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            // acc[r][q] holds column 2 ((q/2 + rot) & 3) + (q & 1): the diagonal entry of row r sits at
-            const int q = 2 * (((r >> 1) - rot) & 3) + (r & 1);
-            double d = 0.0;
-#pragma unroll
-            for (int qq = 0; qq < 8; ++qq) d = (qq == q) ? acc[r][qq] : d;
-            g.diag[8 * t.ti + r] = d;
-        }
+        for (int r = 0; r < 8; ++r) g.diag[8 * t.ti + rot8(r, t.ti)] = acc[r][r];
     }
     if (cold) {
         if (tid < pp) g.v[tid] = tid < p ? 1.0 : 0.0;
@@ -380,12 +388,11 @@ __device__ void eig_wide(const KArgs &a, WGene &g, const WTile &t, const double 
     if (ok != 1) {                                 // uniform across the CTA (and the cluster: same G everywhere)
         // materialise G (both triangles) in the slab for the squaring solver
         if (t.owner) {
-            const int rot = (t.tj >> 1) & 3;
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    const int i = 8 * t.ti + r, j = 8 * t.tj + 2 * (((q >> 1) + rot) & 3) + (q & 1);
+                    const int i = 8 * t.ti + rot8(r, t.ti), j = 8 * t.tj + rot8(q, t.tj);
                     g.Gfull[(long long)i * pp + j] = acc[r][q];
                     g.Gfull[(long long)j * pp + i] = acc[r][q];
                 }
@@ -578,7 +585,7 @@ __global__ void __launch_bounds__(WNT, 1) nmfoa_wide_kernel(const KArgs a) {
     g.nb = pp / 8;
     g.ntiles = g.nb * (g.nb + 1) / 2;
     g.ne = g.ntiles * 64;
-    g.ks = wide_kslices(g.ntiles);
+    g.ks = wide_kslices(g.nb);
     g.seq = 0;
     if (tid == 0) {
         for (int q = 0; q < WIDE_RING; ++q) mbar_init(g.mbar + q, 1);
@@ -599,15 +606,21 @@ __global__ void __launch_bounds__(WNT, 1) nmfoa_wide_kernel(const KArgs a) {
     g.resb = g.M + (long long)g.cs_col * wcols;
     g.tb = g.resb + wcols;
     WTile t;
-    {   // this thread's Gram tile: tiles are numbered row-major over the upper triangle; k-slice = tid / ntiles
-        t.ks = tid / g.ntiles;
-        t.tile = t.ks < g.ks ? tid - t.ks * g.ntiles : -1;
+    {   // this thread's Gram tile.  Lane slots run row-major over the upper triangle, every tile row padded to an even
+        // number of slots (the pad slot stays idle): aligned lane pairs then share the tile row.  k-slice = tid / slots.
+        const int nslots = wide_slots(g.nb);
+        t.ks = tid / nslots;
+        t.tile = -1;
         t.ti = 0; t.tj = 0;
-        if (t.tile >= 0) {
-            int rest = t.tile;
+        if (t.ks < g.ks) {
+            int rest = tid - t.ks * nslots;
             for (int ti = 0; ti < g.nb; ++ti) {
-                if (rest < g.nb - ti) { t.ti = ti; t.tj = ti + rest; break; }
-                rest -= g.nb - ti;
+                const int len = g.nb - ti, padded = len + (len & 1);
+                if (rest < padded) {
+                    if (rest < len) { t.ti = ti; t.tj = ti + rest; t.tile = tile_index(g.nb, ti, t.tj); }
+                    break;
+                }
+                rest -= padded;
             }
         }
         t.owner = t.tile >= 0 && t.ks == 0;

@@ -51,7 +51,24 @@ __global__ void __launch_bounds__(256) probe_lds_kernel(int pattern, int iters, 
         case 6: off = (lane & 15); break;                // 16 distinct (256 B), halves identical
         case 7: off = (lane >> 1); break;                // 16 distinct, lane pairs share
         case 8: off = (lane >> 4) * 8; break;            // 2 distinct, one per half-warp
-        default: off = lane * 5; break;                  // stride 80 B (the P + 2 column stride of P = 8)
+        case 9: off = lane * 5; break;                   // stride 80 B (the P + 2 column stride of P = 8)
+        default: {
+            // patterns 10 .. 13: operand fetches of a 48 x 48 Gram triangle cut into 30 tiles of 8 rows x 6 columns,
+            // tiles numbered row-major with rows of odd length padded so that aligned lane pairs share the row block
+            int rb = 0, cb = 0, slot = 0;
+            bool found = false;
+            for (int r = 0; r < 6 && !found; ++r) {
+                const int c_lo = (8 * r - 5 + 5) / 6;                  // first column block with 6 cb + 5 >= 8 r
+                const int cnt = 8 - c_lo;
+                for (int c = 0; c < cnt + (cnt & 1); ++c, ++slot)
+                    if (slot == lane) { rb = r; cb = c_lo + (c < cnt ? c : cnt - 1); found = true; }
+            }
+            if (pattern == 10) off = 4 * rb;                                   // row operands, 64-byte blocks
+            else if (pattern == 11) off = 4 * rb + ((rb >> 1) & 3);            // the same, fetch order rotated
+            else if (pattern == 12) off = 3 * cb;                              // column operands, 48-byte blocks
+            else off = 3 * lane;                                               // 32 distinct 48-byte blocks
+            break;
+        }
     }
     const unsigned base = (unsigned)__cvta_generic_to_shared(sh) + 16u * (unsigned)off;
     unsigned s0 = 0u;

@@ -2,6 +2,7 @@
 // streamed kernels (nmfoa_mid.cuh, nmfoa_wide.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <stdio.h>
 
 namespace {
 
@@ -22,18 +23,32 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, u
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+__device__ __forceinline__ bool mbar_try(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "MBAR_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra MBAR_DONE;\n"
-        "bra MBAR_WAIT;\n"
-        "MBAR_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
+}
+// Waits for the phase of `bar` with this parity.  A wait that lasts seconds can only be a protocol error (a chunk that
+// was never requested, a lost arrival): the kernel then stops with a message instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 1023u) == 0u && clock64() - t0 > 8000000000ll) {
+            printf("degnorm_b200: mbarrier wait timed out (block %d thread %d barrier +%u parity %u)\n", (int)blockIdx.x,
+                   (int)threadIdx.x, smem_u32(bar) & 0xffffu, parity);
+            __trap();
+        }
+    }
 }
 // generic-proxy accesses (ordinary loads / stores, already ordered by a barrier) before async-proxy (TMA) accesses
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }

@@ -41,7 +41,7 @@ def fp64_peak(device, iters=4096, ctas_per_sm=8, repeats=3):
         return dict(tflops=tflops, dfma_per_clk_per_sm=per_clk, sm_mhz_assumed=mhz, sm_count=sm, ms=best)
 
 
-def lds_wavefronts(device, patterns=range(10), iters=2000):
+def lds_wavefronts(device, patterns=range(14), iters=2000):
     """{pattern: SM cycles per warp-level 128-bit shared load} with 8 warps of one CTA per SM issuing back to back
     (= shared-memory wavefronts per request once the pipe is the bottleneck)."""
     dev = torch.device(device)

@@ -136,7 +136,7 @@ def main():
     p = cfg["p"]
     lengths = stratified_lengths(args.config, args.genes)
     lengths = np.random.default_rng(5).permutation(lengths)        # blocks should not be sorted by length
-    mats, reads = synth_numpy(args.genes, p, cfg["seed"] + 501, lengths=lengths)
+    mats, reads = synth_numpy(args.genes, p, cfg["seed"] + 501, lengths=lengths, jitter=1.0e-6)   # (no exact ties: DESIGN.md section 2)
     reads = np.maximum(reads, 1.0)
     out = dict(config=args.config, samples=p, genes=args.genes, workers=args.workers, cores=os.cpu_count(),
                lengths=dict(min=int(lengths.min()), median=float(np.median(lengths)), max=int(lengths.max()),

@@ -99,3 +99,34 @@ def test_same_as_the_reference_loader_when_it_is_importable(tmp_path):
     assert ours["sample_ids"] == ref["sample_ids"]
     pd.testing.assert_frame_equal(ours["read_count_df"], ref["read_count_df"])
     pd.testing.assert_frame_equal(ours["genes_df"], ref["genes_df"])
+
+
+@pytest.mark.gpu
+def test_streamed_to_device_equals_host_path_and_runs(tmp_path):
+    """load_from_previous(device=...): chromosome-by-chromosome upload overlapped with reading the next pickle; the
+    resident coverage equals the host path's buffer bit for bit, in the same gene order, and GeneNMFOA.run takes it."""
+    import torch
+    from degnorm_b200 import GeneNMFOA
+    from degnorm_b200.packing import pack_coverage
+    from degnorm_b200.warm_start import load_from_previous
+    old = tmp_path / "old"
+    os.makedirs(old)
+    _fake_run_dir(old)
+    os.makedirs(tmp_path / "a")
+    os.makedirs(tmp_path / "b")
+    host = load_from_previous(str(old), str(tmp_path / "a"))
+    dev = load_from_previous(str(old), str(tmp_path / "b"), device="cuda:0")
+    dc = dev["gene_cov_dict"]
+    assert dc.keys() == list(host["gene_cov_dict"].keys()) and dc.p == 3
+    flat, off = pack_coverage(list(host["gene_cov_dict"].values()), 3, pin=False)
+    assert dc.offsets.tolist() == off.tolist() and dc.flat.is_cuda
+    np.testing.assert_array_equal(dc.flat.cpu().numpy(), flat.numpy())
+    assert dev["read_count_df"].equals(host["read_count_df"]) and dev["genes_df"].equals(host["genes_df"])
+    assert os.path.isfile(tmp_path / "b" / "chr2" / "coverage_matrices_chr2.pkl")
+    kw = dict(degnorm_iter=1, nmf_iter=5, min_high_coverage=5)
+    reads = host["read_count_df"][host["sample_ids"]].values.astype(float)
+    m_host, m_dev = GeneNMFOA(**kw), GeneNMFOA(**kw)
+    m_host.run(host["gene_cov_dict"], reads)
+    m_dev.run(dc, reads)
+    np.testing.assert_array_equal(m_host.rho, m_dev.rho)
+    np.testing.assert_array_equal(m_host.x_adj, m_dev.x_adj)
