@@ -182,7 +182,17 @@ def run_cpu_baseline(cfg, kw, n_sample, cores, full=False, seed_shift=0):
     reads = np.maximum(reads, 1.0)
     t_init, t_iter, wall, n_run = cpu_reference_run(mats, reads, kw, cores, full)
     core_s = float((t_init + kw["degnorm_iter"] * t_iter).sum())
+    # how the port compares with the UNMODIFIED reference on the same genes: measured in the build container, where
+    # /root/reference is importable (oracle/time_reference.py -> profiles/r02_cpu_reference_<config>.json)
+    ratio, ratio_src = None, None
+    try:
+        rj = json.load(open(os.path.join(ROOT, "profiles", "r02_cpu_reference_%s.json" % cfg["name"])))
+        ratio, ratio_src = float(rj["port_over_reference_speed"]), "profiles/r02_cpu_reference_%s.json" % cfg["name"]
+    except Exception:
+        pass
     return dict(value=cores * n_sample / core_s, unit=UNIT, cores=cores, kind="port",
+                port_over_reference_speed=ratio, port_over_reference_source=ratio_src,
+                unmodified_reference_estimate=(cores * n_sample / core_s / ratio) if ratio else None,
                 core_seconds_per_gene=core_s / n_sample, wall_seconds=wall, outer_iterations_timed=n_run,
                 sample="%d genes drawn like %s (%d samples, downsample_rate %d), oracle port with scipy svds (the "
                        "reference's own third-party call), fork pool of %d single-threaded workers over genes; init "

@@ -292,10 +292,11 @@ int dn_make_plan(const dn_params *prm, int64_t max_cols, int32_t n_work, int32_t
         // ---- mid-p path (13..48 samples): streamed kernel, optional cluster per gene
         int cl = cluster > 1 ? cluster : 1;
         if (cl != 1 && cl != 2 && cl != 4 && cl != 8 && cl != 16) return fail(DN_ERR_INVALID, "cluster must be 1, 2, 4, 8 or 16%s");
-        // warps = 4: two 4-warp CTAs per SM; warps = 8: one 8-warp CTA per SM, every warp updates and accumulates;
-        // anything else (default): the warp-specialised instantiation, 8 Gram warps + 4 update warps
+        // default (warps = 0 or 8): one 8-warp CTA per SM, every warp updates and accumulates its own columns (measured
+        // fastest: profiles/); warps = 4: two 4-warp CTAs per SM; warps = 12: the warp-specialised instantiation,
+        // 8 Gram warps + 4 update warps
         const int nw = warps == 4 ? 4 : MID_WARPS;
-        const int na = (warps == 4 || warps == 8) ? 0 : MID_UPD_WARPS;
+        const int na = warps == 12 ? MID_UPD_WARPS : 0;
         const int chunk = na > 0 ? MID_WS_CHUNK : mid_chunk(nw);
         long long share = (max_cols + cl - 1) / cl;
         share = (share + chunk - 1) / chunk * chunk;

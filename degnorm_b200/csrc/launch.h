@@ -118,8 +118,13 @@ constexpr int MID_P = 48;             // samples padded to this
 constexpr int MID_WARPS = 8;          // Gram warps per CTA
 constexpr int MID_UPD_WARPS = 4;      // update warps of the warp-specialised instantiation
 constexpr int MID_RING = 3;           // ring stages (RING - 1 chunks in flight)
-constexpr int MID_WS_CHUNK = 32;      // warp-specialised instantiation: columns per ring stage ...
-constexpr int MID_WS_RING = 6;        // ... and stages (same bytes as 3 stages of 64 columns)
+#ifndef MID_WS_CHUNK_COLS             // (tuning builds: -DMID_WS_CHUNK_COLS=64 -DMID_WS_STAGES=3 -DMID_WS_LAG=1)
+#define MID_WS_CHUNK_COLS 32
+#define MID_WS_STAGES 6
+#define MID_WS_LAG 3
+#endif
+constexpr int MID_WS_CHUNK = MID_WS_CHUNK_COLS;   // warp-specialised instantiation: columns per ring stage ...
+constexpr int MID_WS_RING = MID_WS_STAGES;        // ... and stages (same bytes as 3 stages of 64 columns)
 constexpr int MID_NE = 30 * 48;       // partial Gram sums (30 tiles of 6 x 8)
 __host__ __device__ constexpr int mid_chunk(int nw) { return 8 * nw; }   // columns per ring stage
 
@@ -134,7 +139,7 @@ __host__ __device__ inline MidCarve mid_carve(int nw) {
     c.alive = o; o += DN_MAX_BINS / 2;
     c.ibuf = o;  o += 16;
     c.lw = o;    o += DN_MAX_BINS / 2;
-    c.tab = o;   o += 32;
+    c.tab = o;   o += 96;                       // 32 lane slots x 4 ints + 30 tiles x 2 ints (nmfoa_mid.cuh)
     c.mbar = o;  o += 16;                       // "chunk landed" + "chunk updated" mbarriers (up to 6 + 6)
     const long long stage = 2ll * mid_chunk(nw) * (MID_P + 2);
     // 4-warp CTAs (two per SM): G lives in the ring's last stage, which is free between two passes (the ring is

@@ -63,12 +63,21 @@ constexpr int MCPR = MNT / 4;             // columns per CTA step where 4 lanes 
 #ifndef WS_SETMAXNREG
 #define WS_SETMAXNREG 2
 #endif
+constexpr int WS_LAG = MID_WS_LAG;    // bulk stores an update warp keeps in flight (< ring stages - 2)
 constexpr int WS_REG_BASE = 168, WS_REG_B = 184, WS_REG_A = 136;   // see gram_mid_ws: 128 (168 - A) >= 256 (B - 168)
 constexpr int IB_WCOUNT = 1;              // ibuf slots: [0] queue ticket, [1 .. 12] per-warp counts, [20] eigen flag,
 constexpr int IB_EIG = 20;                //             [24 .. 29] consumers done with a ring stage
 constexpr int IB_FREE = 24;
-constexpr int MNTILE = 30;                // 6 x 8 tiles covering the upper triangle of 48 x 48
+// Gram tiles: 30 tiles of 8 rows x 6 columns cover the upper triangle of 48 x 48 (row block rb, column block cb with
+// 6 cb + 5 >= 8 rb).  They are dealt to the 32 lanes row-major with every tile row padded to an even length (two pad
+// slots in all), so that the two lanes of an aligned pair share their ROW operands: a half-warp whose pairs read the
+// same 16 bytes is served in one shared-memory wavefront instead of two (measured with tools/probe_peaks.py), which
+// takes a column's operand fetch from 28 wavefronts (6 x 8 tiles, 7 loads of 4) to 20 (4 row loads of 2 + 3 column
+// loads of 4).  Row pairs are fetched in an order rotated by (rb / 2) so that the row blocks of a half-warp (64 bytes
+// apart) fall into different banks; the column blocks are 48 bytes apart and need no rotation.
+constexpr int MNTILE = 30;
 constexpr int MNE = MNTILE * 48;          // partial sums per warp / CTA
+__device__ __forceinline__ int mrot8(int r, int rb) { return 2 * (((r >> 1) + ((rb >> 1) & 3)) & 3) + (r & 1); }
 
 struct MGene {
     double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *red, *binm, *G, *buf, *ring;
@@ -77,7 +86,6 @@ struct MGene {
     long long slot_stride;                        // doubles between consecutive CTAs' slabs
     int n0, n_cur, n0g, n_curg, goff, cs, nb0, nalive;
     int crank, csize, xpar, eig_steps, eig_fallbacks;
-    int r0, c0;                                   // this lane's Gram tile (rows r0.., columns c0..); -1: none
     bool primed;
     unsigned long long *mbar;                      // MID_RING mbarriers (one per ring stage)
     unsigned use0, use1, use2;                      // completed fills per stage (phase parity of its mbarrier)
@@ -94,6 +102,16 @@ __device__ __forceinline__ void ld12(const double *p, double (&x)[12]) {
     const double2 *q = reinterpret_cast<const double2 *>(p);
 #pragma unroll
     for (int i = 0; i < 6; ++i) { const double2 t = q[i]; x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void ld6(const double *p, double (&x)[6]) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const double2 t = q[i]; x[2 * i] = t.x; x[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void st6(double *p, const double (&x)[6]) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) q[i] = make_double2(x[2 * i], x[2 * i + 1]);
 }
 __device__ __forceinline__ void st12(double *p, const double (&x)[12]) {
     double2 *q = reinterpret_cast<double2 *>(p);
@@ -139,38 +157,39 @@ __device__ __forceinline__ FinArgs fin_args(const MGene &g) {
     return f;
 }
 // (returns the exchange-slot parity to use next)
-__device__ __forceinline__ int gram_finish(FinArgs g, double (&acc)[6][8]) {
+__device__ __forceinline__ int gram_finish(FinArgs g, double (&acc)[8][6]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
-    double *mine = g.buf + (long long)(warp & 3) * MNE + lane * 48;
+    const int tile = g.tab[4 * lane + 2];                       // dense tile id of this lane's slot (-1: pad slot)
+    double *mine = g.buf + (long long)(warp & 3) * MNE + (tile >= 0 ? tile : 0) * 48;
     for (int half = MNW / 2; half >= 1; half >>= 1) {
-        if (warp >= half && warp < 2 * half && lane < MNTILE) {
-            double *dst = g.buf + (long long)(warp - half) * MNE + lane * 48;
+        if (warp >= half && warp < 2 * half && tile >= 0) {
+            double *dst = g.buf + (long long)(warp - half) * MNE + tile * 48;
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+            for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int q = 0; q < 8; q += 2)
-                    *reinterpret_cast<double2 *>(dst + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+                for (int q = 0; q < 6; q += 2)
+                    *reinterpret_cast<double2 *>(dst + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
         }
         __syncthreads();
-        if (warp < half && lane < MNTILE) {
+        if (warp < half && tile >= 0) {
 #pragma unroll
-            for (int r = 0; r < 6; ++r)
+            for (int r = 0; r < 8; ++r)
 #pragma unroll
-                for (int q = 0; q < 8; q += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(mine + r * 8 + q);
+                for (int q = 0; q < 6; q += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(mine + r * 6 + q);
                     acc[r][q] += t.x;
                     acc[r][q + 1] += t.y;
                 }
         }
         __syncthreads();
     }
-    if (warp == 0 && lane < MNTILE) {
+    if (warp == 0 && tile >= 0) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r)
+        for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int q = 0; q < 8; q += 2)
-                *reinterpret_cast<double2 *>(g.buf + lane * 48 + r * 8 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+            for (int q = 0; q < 6; q += 2)
+                *reinterpret_cast<double2 *>(g.buf + tile * 48 + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
     }
     __syncthreads();
     // ---- cluster sum (rank order) and scatter into the square G
@@ -193,8 +212,9 @@ __device__ __forceinline__ int gram_finish(FinArgs g, double (&acc)[6][8]) {
             for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + e);
         }
         const int t = e / 48, rq = e - t * 48;
-        const int c0t = g.tab[2 * t + 1], q = rq & 7;
-        const int i = g.tab[2 * t] + rq / 8, j = c0t + 2 * (((q >> 1) + (c0t >> 4)) & 3) + (q & 1);
+        const int r0t = g.tab[128 + 2 * t], c0t = g.tab[128 + 2 * t + 1];     // (row, column) offset of dense tile t
+        const int r = rq / 6, q = rq - 6 * r;
+        const int i = r0t + mrot8(r, r0t >> 3), j = c0t + q;
         if (i <= j) {
             g.G[i * MP + j] = s;
             g.G[j * MP + i] = s;
@@ -213,20 +233,20 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     const int nchunk = (n + MCH - 1) / MCH;
     constexpr int STG = 2 * MCH * MCS;                     // doubles per ring stage (M then x)
     const double c = a.c;
-    double acc[6][8];
+    double acc[8][6];
 #pragma unroll
-    for (int r = 0; r < 6; ++r)
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
+        for (int q = 0; q < 6; ++q) acc[r][q] = 0.0;
     double vq[12];
     const int q4 = tid & 3;
     if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
     // this lane's tile, read from the shared table (a load is not rematerialised inside the chunk loop)
-    const int tr0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane) : -1;
-    const int tc0 = lane < MNTILE ? *reinterpret_cast<volatile int *>(g.tab + 2 * lane + 1) : 0;
-    const int rot = tc0 >> 4;
-    const int uo0 = tc0 + 2 * ((0 + rot) & 3), uo1 = tc0 + 2 * ((1 + rot) & 3), uo2 = tc0 + 2 * ((2 + rot) & 3),
-              uo3 = tc0 + 2 * ((3 + rot) & 3);
+    const int tr0 = *reinterpret_cast<volatile int *>(g.tab + 4 * lane + 2) >= 0
+                        ? *reinterpret_cast<volatile int *>(g.tab + 4 * lane) : -1;
+    const int tc0 = *reinterpret_cast<volatile int *>(g.tab + 4 * lane + 1);
+    const int ao0 = tr0 + mrot8(0, tr0 >> 3), ao1 = tr0 + mrot8(2, tr0 >> 3), ao2 = tr0 + mrot8(4, tr0 >> 3),
+              ao3 = tr0 + mrot8(6, tr0 >> 3);
 
     // One thread hands a chunk (25.6 KB of M, and of x for an update pass) to the TMA unit; the bytes land in the
     // ring stage and complete the stage's mbarrier.  Callers guarantee (by a __syncthreads) that nobody still uses
@@ -318,22 +338,22 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
 #define MID_LOADP(S, col)                                                                   \
     {                                                                                       \
         const double *mc_ = sM + (col) * MCS;                                               \
-        S##a0 = *reinterpret_cast<const double2 *>(mc_ + tr0);                              \
-        S##a1 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 2);                          \
-        S##a2 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 4);                          \
-        S##u0 = *reinterpret_cast<const double2 *>(mc_ + uo0);                              \
-        S##u1 = *reinterpret_cast<const double2 *>(mc_ + uo1);                              \
-        S##u2 = *reinterpret_cast<const double2 *>(mc_ + uo2);                              \
-        S##u3 = *reinterpret_cast<const double2 *>(mc_ + uo3);                              \
+        S##a0 = *reinterpret_cast<const double2 *>(mc_ + ao0);                              \
+        S##a1 = *reinterpret_cast<const double2 *>(mc_ + ao1);                              \
+        S##a2 = *reinterpret_cast<const double2 *>(mc_ + ao2);                              \
+        S##a3 = *reinterpret_cast<const double2 *>(mc_ + ao3);                              \
+        S##u0 = *reinterpret_cast<const double2 *>(mc_ + tc0);                              \
+        S##u1 = *reinterpret_cast<const double2 *>(mc_ + tc0 + 2);                          \
+        S##u2 = *reinterpret_cast<const double2 *>(mc_ + tc0 + 4);                          \
     }
 #define MID_FMAP(S)                                                                         \
     {                                                                                       \
-        const double ar_[6] = {S##a0.x, S##a0.y, S##a1.x, S##a1.y, S##a2.x, S##a2.y};       \
-        const double uc_[8] = {S##u0.x, S##u0.y, S##u1.x, S##u1.y, S##u2.x, S##u2.y, S##u3.x, S##u3.y}; \
-        _Pragma("unroll") for (int r = 0; r < 6; ++r)                                       \
-            _Pragma("unroll") for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar_[r], uc_[q], acc[r][q]); \
+        const double ar_[8] = {S##a0.x, S##a0.y, S##a1.x, S##a1.y, S##a2.x, S##a2.y, S##a3.x, S##a3.y}; \
+        const double uc_[6] = {S##u0.x, S##u0.y, S##u1.x, S##u1.y, S##u2.x, S##u2.y};       \
+        _Pragma("unroll") for (int r = 0; r < 8; ++r)                                       \
+            _Pragma("unroll") for (int q = 0; q < 6; ++q) acc[r][q] = fma(ar_[r], uc_[q], acc[r][q]); \
     }
-            double2 Aa0, Aa1, Aa2, Au0, Au1, Au2, Au3, Ba0, Ba1, Ba2, Bu0, Bu1, Bu2, Bu3;
+            double2 Aa0, Aa1, Aa2, Aa3, Au0, Au1, Au2, Ba0, Ba1, Ba2, Ba3, Bu0, Bu1, Bu2;
             // Two columns per trip: 14 loads, then 96 FMAs (the shared-load latency is paid once per pair).
             // (Keeping the next column's operands in flight behind this column's FMAs measured no faster: the
             // phase is bound by shared-memory wavefronts, 28 per column for the 6 x 8 tiles, not by load latency.)
@@ -420,9 +440,8 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
         if (with_x) bulk_g2s(dst + MCH * MCS, g.X + (long long)ch * (MCH * MCS), CHB, full + st);
     };
     // one consumer (a B warp, or an A warp whose bulk store has read the stage) is done with chunk ch; called by lane 0
-    auto release = [&](int ch) {
+    auto release = [&](int ch, unsigned st) {
         if (ch + MRING < nchunk) {
-            const unsigned st = (seq0 + (unsigned)ch) % MRING;
             __threadfence_block();
             const int old = atomicAdd(const_cast<int *>(freec + st), 1);
             if (old == MNW + MNA - 1) {
@@ -436,26 +455,28 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
         if (tid == 0)
             for (int q = 0; q < MRING && q < nchunk; ++q) issue(q, UPDATE);
     }
-    double acc[6][8];
-#pragma unroll
-    for (int r = 0; r < 6; ++r)
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
+    // (the accumulators are zeroed inside each role's branch -- at its start for the Gram warps, at its END for the
+    // update warps -- so that they are not live through the update code, whose 36 doubles of column data would
+    // otherwise be spilled: local memory has next to no L1 beside 224 KB of shared memory)
+    double acc[8][6];
 
     if (is_b) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[r][q] = 0.0;
         // -------------------------------------------------------------------------------------------- Gram warps
 #if WS_SETMAXNREG >= 2
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(WS_REG_B));
 #endif
-        const int tr0 = lane < MNTILE ? g.fin.tab[2 * lane] : -1;
-        const int tc0 = lane < MNTILE ? g.fin.tab[2 * lane + 1] : 0;
-        const int rot = tc0 >> 4;
-        const int uo0 = tc0 + 2 * ((0 + rot) & 3), uo1 = tc0 + 2 * ((1 + rot) & 3), uo2 = tc0 + 2 * ((2 + rot) & 3),
-                  uo3 = tc0 + 2 * ((3 + rot) & 3);
+        const int tr0 = g.fin.tab[4 * lane + 2] >= 0 ? g.fin.tab[4 * lane] : -1;
+        const int tc0 = g.fin.tab[4 * lane + 1];
+        const int ao0 = tr0 + mrot8(0, tr0 >> 3), ao1 = tr0 + mrot8(2, tr0 >> 3), ao2 = tr0 + mrot8(4, tr0 >> 3),
+                  ao3 = tr0 + mrot8(6, tr0 >> 3);
+        unsigned st = seq0 % MRING, par = (seq0 / MRING) & 1u;
 #pragma unroll 1
         for (int ch = 0; ch < nchunk; ++ch) {
-            const unsigned k = seq0 + (unsigned)ch, st = k % MRING;
-            mbar_wait(upd + st, (k / MRING) & 1u);
+            mbar_wait(upd + st, par);
             const double *sM = g.ring + st * STG;
             const int ncol = min(MCH, n - ch * MCH);
             if (tr0 >= 0) {
@@ -464,22 +485,22 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
 #define MID_LOADP(S, col)                                                                   \
     {                                                                                       \
         const double *mc_ = sM + (col) * MCS;                                               \
-        S##a0 = *reinterpret_cast<const double2 *>(mc_ + tr0);                              \
-        S##a1 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 2);                          \
-        S##a2 = *reinterpret_cast<const double2 *>(mc_ + tr0 + 4);                          \
-        S##u0 = *reinterpret_cast<const double2 *>(mc_ + uo0);                              \
-        S##u1 = *reinterpret_cast<const double2 *>(mc_ + uo1);                              \
-        S##u2 = *reinterpret_cast<const double2 *>(mc_ + uo2);                              \
-        S##u3 = *reinterpret_cast<const double2 *>(mc_ + uo3);                              \
+        S##a0 = *reinterpret_cast<const double2 *>(mc_ + ao0);                              \
+        S##a1 = *reinterpret_cast<const double2 *>(mc_ + ao1);                              \
+        S##a2 = *reinterpret_cast<const double2 *>(mc_ + ao2);                              \
+        S##a3 = *reinterpret_cast<const double2 *>(mc_ + ao3);                              \
+        S##u0 = *reinterpret_cast<const double2 *>(mc_ + tc0);                              \
+        S##u1 = *reinterpret_cast<const double2 *>(mc_ + tc0 + 2);                          \
+        S##u2 = *reinterpret_cast<const double2 *>(mc_ + tc0 + 4);                          \
     }
 #define MID_FMAP(S)                                                                         \
     {                                                                                       \
-        const double ar_[6] = {S##a0.x, S##a0.y, S##a1.x, S##a1.y, S##a2.x, S##a2.y};       \
-        const double uc_[8] = {S##u0.x, S##u0.y, S##u1.x, S##u1.y, S##u2.x, S##u2.y, S##u3.x, S##u3.y}; \
-        _Pragma("unroll") for (int r = 0; r < 6; ++r)                                       \
-            _Pragma("unroll") for (int q = 0; q < 8; ++q) acc[r][q] = fma(ar_[r], uc_[q], acc[r][q]); \
+        const double ar_[8] = {S##a0.x, S##a0.y, S##a1.x, S##a1.y, S##a2.x, S##a2.y, S##a3.x, S##a3.y}; \
+        const double uc_[6] = {S##u0.x, S##u0.y, S##u1.x, S##u1.y, S##u2.x, S##u2.y};       \
+        _Pragma("unroll") for (int r = 0; r < 8; ++r)                                       \
+            _Pragma("unroll") for (int q = 0; q < 6; ++q) acc[r][q] = fma(ar_[r], uc_[q], acc[r][q]); \
     }
-                double2 Aa0, Aa1, Aa2, Au0, Au1, Au2, Au3, Ba0, Ba1, Ba2, Bu0, Bu1, Bu2, Bu3;
+                double2 Aa0, Aa1, Aa2, Aa3, Au0, Au1, Au2, Ba0, Ba1, Ba2, Ba3, Bu0, Bu1, Bu2;
 #pragma unroll 1
                 for (; cc + 1 < cend; cc += 2) {
                     MID_LOADP(A, cc);
@@ -495,7 +516,8 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
 #undef MID_FMAP
             }
             __syncwarp();
-            if (lane == 0) release(ch);
+            if (lane == 0) release(ch, st);
+            if (++st == MRING) { st = 0; par ^= 1u; }
         }
 #if WS_SETMAXNREG >= 2
         // (the warps of a warpgroup synchronise between two setmaxnreg instructions, as PTX requires)
@@ -510,10 +532,12 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
 #endif
         const int aw = warp - MNW;                            // this warp's columns of a chunk: [CPA aw, CPA (aw + 1))
         constexpr int CPA = MCH / (MNA > 0 ? MNA : 1);
-        const int q4 = lane & 3;
+        // 8 lanes per column, 6 rows each: 18 doubles of column data per thread (12 rows per lane would not fit the
+        // registers an update warp keeps during the pass, and local memory has next to no L1 here)
+        const int q8 = lane & 7;
         const double c = g.c;
-        double vq[12];
-        if constexpr (UPDATE) ld12(g.v + 12 * q4, vq);
+        double vq[6];
+        if constexpr (UPDATE) ld6(g.v + 6 * q8, vq);
 #pragma unroll 1
         for (int ch = 0; ch < nchunk; ++ch) {
             const unsigned k = seq0 + (unsigned)ch, st = k % MRING;
@@ -522,30 +546,31 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
             const int ncol = min(MCH, n - ch * MCH);
             if constexpr (UPDATE) {
 #pragma unroll 1
-                for (int rd = 0; rd < CPA / 8; ++rd) {
-                    const int cc = aw * CPA + rd * 8 + (lane >> 2);
+                for (int rd = 0; rd < CPA / 4; ++rd) {
+                    const int cc = aw * CPA + rd * 4 + (lane >> 3);
                     const bool act = cc < ncol;
-                    double m[12], x[12];
+                    double m[6], x[6];
                     double tp = 0.0;
                     if (act) {
-                        ld12(sM + cc * MCS + 12 * q4, m);
-                        ld12(sM + MCH * MCS + cc * MCS + 12 * q4, x);
+                        ld6(sM + cc * MCS + 6 * q8, m);
+                        ld6(sM + MCH * MCS + cc * MCS + 6 * q8, x);
                         double t0 = 0.0, t1 = 0.0;
 #pragma unroll
-                        for (int i = 0; i < 12; i += 2) { t0 = fma(vq[i], m[i], t0); t1 = fma(vq[i + 1], m[i + 1], t1); }
+                        for (int i = 0; i < 6; i += 2) { t0 = fma(vq[i], m[i], t0); t1 = fma(vq[i + 1], m[i + 1], t1); }
                         tp = t0 + t1;
                     }
                     double t = tp;
                     t += __shfl_xor_sync(0xffffffffu, t, 1);
                     t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    t += __shfl_xor_sync(0xffffffffu, t, 4);
                     if (act) {
 #pragma unroll
-                        for (int i = 0; i < 12; ++i) {
+                        for (int i = 0; i < 6; ++i) {
                             const double res = fma(vq[i], t, -x[i]);
                             const double w = fma(-c, res, m[i] - x[i]);
                             m[i] = fma(0.5, w + fabs(w), x[i]);
                         }
-                        st12(sM + cc * MCS + 12 * q4, m);
+                        st6(sM + cc * MCS + 6 * q8, m);
                     }
                 }
                 fence_proxy_async_smem();                     // the stage is read by this warp's bulk store below
@@ -561,10 +586,13 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
                                      "r"(smem_u32(sM + c0 * MCS)), "r"((unsigned)(nmine * MCS * 8))
                                      : "memory");
                     asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-                    bulk_wait_read<1>();                      // the store of the previous chunk has read its stage
-                    if (ch >= 1) release(ch - 1);
+                    // The stage of chunk ch - WS_LAG is released once the store issued WS_LAG chunks ago has read it:
+                    // waiting for the store just issued would put a TMA round trip into every chunk of this warp
+                    // (measured: the update warps then set the pace of the pass).
+                    bulk_wait_read<WS_LAG>();
+                    if (ch >= WS_LAG) release(ch - WS_LAG, (seq0 + (unsigned)(ch - WS_LAG)) % MRING);
                 } else {
-                    release(ch);
+                    release(ch, st);
                 }
             }
         }
@@ -572,6 +600,10 @@ __device__ __forceinline__ PassOut gram_mid_ws(const PassArgs g, const bool prim
             if (lane == 0) bulk_wait_all();                   // the slab holds this warp's columns of the new M
         }
         __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc[r][q] = 0.0;
 #if WS_SETMAXNREG >= 2
         // The update warps take their registers back only after every Gram warp has returned its surplus (named
         // barrier 4, all threads).  Re-acquiring at the end of their own loop deadlocks on short passes: an update
@@ -866,16 +898,22 @@ __global__ void __launch_bounds__(MNT, MNW <= 4 ? 2 : 1) nmfoa_mid_kernel(const 
     g.M = g.X + (long long)MCS * wcols;
     g.resb = g.M + (long long)MCS * wcols;
     g.tb = g.resb + wcols;
-    {   // Gram tile of this lane (same in every warp) and the table of all tiles
-        int idx = 0;
-        g.r0 = -1; g.c0 = 0;
-        for (int rb = 0; rb < 8; ++rb)
-            for (int cb = 0; cb < 6; ++cb)
-                if (8 * cb + 7 >= 6 * rb) {
-                    if (idx == lane) { g.r0 = 6 * rb; g.c0 = 8 * cb; }
-                    if (tid == 0) { g.tab[2 * idx] = 6 * rb; g.tab[2 * idx + 1] = 8 * cb; }
-                    ++idx;
-                }
+    if (tid == 0) {
+        // lane slots (4 ints each: row offset, column offset, dense tile id or -1, -) and, from int 128 on, the
+        // (row, column) offsets of the dense tiles
+        int slot = 0, tile = 0;
+        for (int rb = 0; rb < 6; ++rb) {
+            const int c_lo = (8 * rb) / 6, cnt = 8 - c_lo;           // first column block with 6 cb + 5 >= 8 rb
+            for (int c = 0; c < cnt + (cnt & 1); ++c, ++slot) {
+                const bool real = c < cnt;
+                const int cb = c_lo + (real ? c : cnt - 1);
+                g.tab[4 * slot] = 8 * rb;
+                g.tab[4 * slot + 1] = 6 * cb;
+                g.tab[4 * slot + 2] = real ? tile : -1;
+                g.tab[4 * slot + 3] = 0;
+                if (real) { g.tab[128 + 2 * tile] = 8 * rb; g.tab[128 + 2 * tile + 1] = 6 * cb; ++tile; }
+            }
+        }
     }
     for (int e = tid; e < N_SMALL * MP; e += MNT) sm[e] = 0.0;
     for (int e = tid; e < MP * MP; e += MNT) g.G[e] = 0.0;

@@ -113,7 +113,8 @@ int dn_device_info(int32_t *sm_count, int32_t *max_smem_optin, int32_t *cc);
  * for downsample_rate 1, ceil(L/rate) otherwise).  want_resident: shared-memory column capacity wanted
  * (0 forces the streamed path, -1 = as many as fit).  for_init=1 sizes the workspace for dn_init_ratio_svd.
  * warps: warps per CTA on the small-p path (1, 2, 4, 8, 16; 0 = chosen from the tier); on the mid-p path 4 selects
- * the instantiation with two 4-warp CTAs per SM (anything else: 8 warps, one CTA per SM); ignored elsewhere.
+ * the instantiation with two 4-warp CTAs per SM and 12 the warp-specialised one (8 Gram warps + 4 update warps);
+ * anything else: 8 warps, one CTA per SM (the default); ignored elsewhere.
  * cluster: CTAs that share one gene on the small-p path (0/1: none; 2, 4, 8, 16: a thread-block cluster whose
  * CTAs each hold ceil(max_cols/cluster) columns and exchange the partial Gram through distributed shared memory).
  * For 13..48 samples the streamed mid-p kernel is planned (cluster 1..16); cluster = -1 asks for the generic tiled

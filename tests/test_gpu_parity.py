@@ -285,12 +285,13 @@ def test_cluster_path_equals_single_cta_path(p, cluster, streamed):
 
 
 @pytest.mark.parametrize("p,cluster,warps", [(17, 1, 0), (48, 1, 0), (48, 2, 0), (48, 4, 0), (30, 16, 0),
-                                             (48, 1, 8), (30, 16, 8), (48, 1, 4), (17, 2, 4), (30, 16, 4)])
+                                             (48, 1, 12), (17, 2, 12), (48, 8, 12), (30, 16, 12),
+                                             (48, 1, 4), (17, 2, 4), (30, 16, 4)])
 def test_mid_kernel_equals_tiled_kernel(p, cluster, warps):
-    """13..48 samples: the streamed mid-p kernel (warps = 0: the default warp-specialised instantiation, 8 Gram warps
-    + 4 update warps; 8: every warp updates and accumulates; 4: two 4-warp CTAs per SM; optionally one cluster per
-    gene) against the generic tiled kernel on the same genes: identical decisions and call sequences, DI equal to
-    rounding."""
+    """13..48 samples: the streamed mid-p kernel (warps = 0: the default, 8 warps that update and accumulate their own
+    columns; 12: the warp-specialised instantiation, 8 Gram warps + 4 update warps; 4: two 4-warp CTAs per SM;
+    optionally one cluster per gene) against the generic tiled kernel on the same genes: identical decisions and call
+    sequences, DI equal to rounding."""
     import torch
     from degnorm_b200.engine import Params, ShardEngine
     from degnorm_b200.packing import pack_coverage
@@ -307,7 +308,7 @@ def test_mid_kernel_equals_tiled_kernel(p, cluster, warps):
         eng.force_cluster = cluster if (use_mid and cluster > 1) else 0
         eng.load(flat.cuda(), off, torch.from_numpy(reads).cuda())
         assert all((int(b.plan.tile) == 6) == use_mid for b in eng.buckets)
-        assert not use_mid or all(int(b.plan.threads) == (384 if warps == 0 else 32 * warps) for b in eng.buckets)
+        assert not use_mid or all(int(b.plan.threads) == (256 if warps == 0 else 32 * warps) for b in eng.buckets)
         o = eng.run(None, want_estimates=True)
         torch.cuda.synchronize()
         outs.append({k: v.cpu().numpy() for k, v in o.items() if torch.is_tensor(v)})

@@ -299,9 +299,9 @@ def test_device_coverage_handle_filters_like_filter_genes_on_host_tensors():
 
 
 def test_mid_kernel_plans_are_pure_host_arithmetic():
-    """dn_make_plan for 13..48 samples (no device call): the default warp-specialised instantiation (8 Gram warps +
-    4 update warps) and the 8-warp one take one CTA per SM with a 3 x 51.2 KB ring, the 4-warp one fits two CTAs per
-    SM (G parked in the free ring stage); workspace columns are whole chunks; clusters divide the CTA count."""
+    """dn_make_plan for 13..48 samples (no device call): the default 8-warp instantiation and the warp-specialised
+    one (8 Gram warps + 4 update warps, warps = 12) take one CTA per SM with a 153.6 KB ring, the 4-warp one fits two
+    CTAs per SM (G parked in the free ring stage); workspace columns are whole chunks; clusters divide the CTA count."""
     import ctypes as C
     from degnorm_b200 import _lib
     from degnorm_b200.engine import Params
@@ -314,10 +314,11 @@ def test_mid_kernel_plans_are_pure_host_arithmetic():
         rc = lib.dn_make_plan(C.byref(prm), max_cols, n_work, 0, 0, warps, cluster, sm, smem, C.byref(pl))
         assert rc == 0, lib.dn_last_error()
         return pl
-    pw = plan(5000, 10000, 0, 1)
+    pw = plan(5000, 10000, 12, 1)
     assert (pw.tile, pw.threads, pw.cluster, pw.ctas) == (6, 384, 1, 148)
-    p8 = plan(5000, 10000, 8, 1)
+    p8 = plan(5000, 10000, 0, 1)
     assert (p8.tile, p8.threads, p8.cluster, p8.ctas) == (6, 256, 1, 148)
+    assert plan(5000, 10000, 8, 1).threads == 256
     assert pw.smem_bytes == p8.smem_bytes and pw.ws_cols == 5024 and pw.ws_cols % 32 == 0    # 32-column chunks, 6 stages
     assert p8.smem_bytes <= smem and 2 * (p8.smem_bytes + 1024) > smem          # one CTA per SM
     assert p8.ws_cols == 5056 and p8.ws_cols % 64 == 0
@@ -326,7 +327,7 @@ def test_mid_kernel_plans_are_pure_host_arithmetic():
     assert 2 * (p4.smem_bytes + 1024) <= smem + 1024                             # two CTAs per SM
     assert p4.ws_cols == 5024 and p4.ws_cols % 32 == 0
     pc = plan(40000, 5, 0, 4)
-    assert (pc.cluster, pc.ctas, pc.ws_cols) == (4, 20, 10016)
+    assert (pc.cluster, pc.ctas, pc.ws_cols) == (4, 20, 10048)
     assert plan(40000, 1000, 0, 16).ctas == 144                                   # 9 clusters of 16 on 148 SMs
     pl = _lib.DnPlan()
     assert lib.dn_make_plan(C.byref(prm), 5000, 10, 0, 0, 0, 3, sm, smem, C.byref(pl)) != 0      # cluster of 3
