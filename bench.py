@@ -315,6 +315,10 @@ def main():
         mine = shards[rank]
         if world == 1:
             cov, off, reads = synth_torch(lengths_all, p, cfg["seed"], dev)
+        elif n_total > 20000:
+            # full-size runs: every rank draws only ITS genes (same lengths as the one-GPU run, own random stream --
+            # drawing all 58 GB on every rank would cost minutes of GPU time per rank for nothing)
+            cov, off, reads = synth_torch(lengths_all[mine], p, cfg["seed"] + 7919 * (rank + 1), dev)
         else:
             cov_all, off_all, reads_all = synth_torch(lengths_all, p, cfg["seed"], dev)
             lengths = lengths_all[mine]
