@@ -44,6 +44,9 @@ namespace {
 #ifndef MID_NA
 #define MID_NA 0
 #endif
+#ifndef MID_B_PIPELINED
+#define MID_B_PIPELINED 1      // phase B software-pipelined (measured +4 % on C3; 0: load two columns, then their FMAs)
+#endif
 // MID_NA > 0: warp-specialised instantiation.  Warps 0 .. MNW-1 ("B warps") only accumulate the Gram matrix, warps
 // MNW .. MNW+MNA-1 ("A warps") only run the multiplier update one chunk ahead of them; nobody waits at a block barrier
 // inside a pass (see gram_mid_ws).
@@ -227,7 +230,9 @@ __device__ __forceinline__ int gram_finish(FinArgs g, double (&acc)[8][6]) {
 
 // ---- one pass over this CTA's columns: (optional multiplier update) + Gram of M -> G (shared, identical cluster-wide)
 template <bool UPDATE>
-__device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
+// m_is_x: lambda is still zero, so this pass reads M from the x array (the first fit and the first update pass of an
+// nmf() call: M = x is never copied; the slab's M is first written by the store-back of the first update pass).
+__device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next, bool m_is_x) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = g.n_cur;
     const int nchunk = (n + MCH - 1) / MCH;
@@ -252,7 +257,8 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     // ring stage and complete the stage's mbarrier.  Callers guarantee (by a __syncthreads) that nobody still uses
     // the stage and that the slab holds the data (ordinary stores of the previous pass): the proxy fence orders
     // those generic-proxy accesses before the async-proxy copy.
-    auto issue = [&](int ch, bool with_x) {
+    const double *msrc = m_is_x ? g.X : g.M;
+    auto issue = [&](int ch, bool with_x, const double *msrc_) {
         if (tid == 0 && ch < nchunk) {
             const int st = ch % MID_RING;
             double *dst = g.ring + st * STG;
@@ -261,7 +267,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             // (the full fence is a MEMBAR.GPU on the issuing warp, which the other seven then wait for: -2 %)
             fence_proxy_async_smem();
             mbar_expect_tx(g.mbar + st, with_x ? 2 * bytes : bytes);
-            bulk_g2s(dst, g.M + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
+            bulk_g2s(dst, msrc_ + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
             if (with_x) bulk_g2s(dst + MCH * MCS, g.X + (long long)ch * (MCH * MCS), bytes, g.mbar + st);
         }
     };
@@ -273,7 +279,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     };
     if (!g.primed) {
 #pragma unroll
-        for (int q = 0; q < MID_RING - 1; ++q) issue(q, UPDATE);
+        for (int q = 0; q < MID_RING - 1; ++q) issue(q, UPDATE, msrc);
     }
     constexpr bool TSTORE = (MID_TMA_STORE != 0) && UPDATE;
     // TSTORE schedule, at the barrier that opens chunk ch: stage (ch - 1) holds that chunk's final M -> bulk store;
@@ -285,13 +291,14 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
         }
     };
     for (int ch = 0; ch < nchunk; ++ch) {
+        if constexpr (TSTORE) fence_proxy_async_smem();    // this thread's phase-A stores of chunk ch - 1 -> async proxy
         __syncthreads();                                   // everyone is done with stage (ch - 1): refill it
         if constexpr (TSTORE) {
             store_back(ch - 1);
             if (tid == 0) bulk_wait_read<1>();
-            if (ch + 1 >= MID_RING - 1) issue(ch + 1, UPDATE);
+            if (ch + 1 >= MID_RING - 1) issue(ch + 1, UPDATE, msrc);
         } else {
-            issue(ch + MID_RING - 1, UPDATE);
+            issue(ch + MID_RING - 1, UPDATE, msrc);
         }
         wait_stage(ch);                                    // chunk ch has landed
         double *sM = g.ring + (ch % MID_RING) * STG;
@@ -321,8 +328,10 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
                     m[i] = fma(0.5, w + fabs(w), x[i]);
                 }
                 st12(sM + cc * MCS + 12 * q4, m);
-                if constexpr (TSTORE) fence_proxy_async_smem();      // the stage is read by the bulk store later
-                else st12(g.M + ((long long)ch * MCH + cc) * MCS + 12 * q4, m);
+                // (TSTORE: the stage is read by the bulk store after the next chunk barrier; the proxy fence that
+                // has to stand between these stores and that copy is taken just before the barrier, when the stores
+                // have long drained, instead of here, where every warp would sit out their latency: 4 % of the samples)
+                if constexpr (!TSTORE) st12(g.M + ((long long)ch * MCH + cc) * MCS + 12 * q4, m);
             }
             __syncwarp();        // phase B of this warp only reads the 8 columns its own lanes just wrote
         }
@@ -357,6 +366,27 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
             // Two columns per trip: 14 loads, then 96 FMAs (the shared-load latency is paid once per pair).
             // (Keeping the next column's operands in flight behind this column's FMAs measured no faster: the
             // phase is bound by shared-memory wavefronts, 28 per column for the 6 x 8 tiles, not by load latency.)
+#if MID_B_PIPELINED
+            // software-pipelined: the operands of the next column are requested before the FMAs of the current one,
+            // so that shared-memory fetch and FP64 issue overlap inside the warp (two operand sets, A and B)
+            if (cc < cend) {
+                MID_LOADP(A, cc);
+#pragma unroll 1
+                for (; cc + 2 < cend; cc += 2) {
+                    MID_LOADP(B, cc + 1);
+                    MID_FMAP(A);
+                    MID_LOADP(A, cc + 2);
+                    MID_FMAP(B);
+                }
+                if (cc + 1 < cend) {
+                    MID_LOADP(B, cc + 1);
+                    MID_FMAP(A);
+                    MID_FMAP(B);
+                } else {
+                    MID_FMAP(A);
+                }
+            }
+#else
 #pragma unroll 1
             for (; cc + 1 < cend; cc += 2) {
                 MID_LOADP(A, cc);
@@ -368,6 +398,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
                 MID_LOADP(A, cc);
                 MID_FMAP(A);
             }
+#endif
 #undef MID_LOADP
 #undef MID_FMAP
         }
@@ -381,7 +412,7 @@ __device__ void gram_mid(const KArgs &a, MGene &g, bool prime_next) {
     g.primed = prime_next;
     if (prime_next) {
 #pragma unroll
-        for (int q = 0; q < MID_RING - 1; ++q) issue(q, true);
+        for (int q = 0; q < MID_RING - 1; ++q) issue(q, true, (!UPDATE && m_is_x) ? g.X : g.M);   // (the pass after the first fit)
     }
     g.xpar = gram_finish(fin_args(g), acc);
 }
@@ -820,7 +851,9 @@ __device__ void final_pass_mid(const KArgs &a, MGene &g, bool first, bool want_r
 
 __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res, double *e_first_g) {
     const int tid = threadIdx.x;
-    {   // lambda = 0: M = x
+    // The default instantiation never copies M = x: the first fit and the first update pass read the x array.
+    constexpr bool NO_COPY = (MNA == 0) && (MID_TMA_STORE != 0);
+    if (!NO_COPY || a.nmf_iter == 0) {   // lambda = 0: M = x
         const double2 *src = reinterpret_cast<const double2 *>(g.X);
         double2 *dst = reinterpret_cast<double2 *>(g.M);
         const long long n2 = (long long)g.n_cur * (MCS / 2);
@@ -846,10 +879,11 @@ __device__ void run_nmf_mid(const KArgs &a, MGene &g, bool first, bool want_res,
             eig_mid(a, g, it < 0);
         }
     } else {
-        gram_mid<false>(a, g, T > 0);
+        const bool lazy_m = NO_COPY && T > 0;
+        gram_mid<false>(a, g, T > 0, lazy_m);
         eig_mid(a, g, true);
         for (int it = 0; it < T; ++it) {
-            gram_mid<true>(a, g, it + 1 < T);
+            gram_mid<true>(a, g, it + 1 < T, lazy_m && it == 0);
             eig_mid(a, g, false);
         }
     }

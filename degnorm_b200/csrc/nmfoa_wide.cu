@@ -192,9 +192,10 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
         }
         // phase B: this thread's tile over the chunk's columns (its k-slice of them)
         if (has_tile) {
+            const double *mc = sM + g.ks * CS;
+            const int mstep = g.nks * CS;
 #pragma unroll 1
-            for (int cc = g.ks; cc < ncol; cc += g.nks) {
-                const double *mc = sM + cc * CS;
+            for (int cc = g.ks; cc < ncol; cc += g.nks, mc += mstep) {
                 const double2 a0 = *reinterpret_cast<const double2 *>(mc + ao0);
                 const double2 a1 = *reinterpret_cast<const double2 *>(mc + ao1);
                 const double2 a2 = *reinterpret_cast<const double2 *>(mc + ao2);
