@@ -301,6 +301,10 @@ class ShardEngine(object):
         prm, p, n, dev, lib = self.prm, self.p, self.n, self.device, self.lib
         f64 = dict(dtype=torch.float64, device=dev)
         main = torch.cuda.current_stream(dev)
+        # the previous run's outputs go first: at C3's full size the estimates are as large as the coverage (74 GiB),
+        # and two generations of them beside it do not fit
+        self.out = None
+        self._e_first = None
         n_iter = prm.degnorm_iter
         nn = max(n, 1)
         est_rs = torch.zeros((nn, p), **f64)
