@@ -1,6 +1,5 @@
 #!/bin/bash
-# full-size C3 (60,000 genes x 48 samples) sharded over the 8 GPUs of one box, device-resident; then the default
-# sample at N = 8 with the end-to-end leg
+# full-size C3 (60,000 genes x 48 samples) sharded over the 8 GPUs of one box, device-resident
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 2000 > gpurun_out/clocks_full8.csv &
@@ -10,7 +9,4 @@ timeout 900 $T bench.py --gpus 8 --genes 60000 --steps 2 --warmup 1 --no-cpu --n
 tail -3 gpurun_out/c3_full_8gpu.err | cut -c1-300
 python -c "
 import json; d=json.load(open('gpurun_out/c3_full_8gpu.json')); print(d['value'], d['ms_per_step'], d['roofline']['frac'], [ (r['genes'], round(r['bs_ms_per_step']), round(r['wait_ms_per_step'])) for r in d['ranks']])"
-timeout 600 $T bench.py --gpus 8 --steps 2 --warmup 1 --no-variants > gpurun_out/c3_sample_8gpu.json 2> gpurun_out/c3_sample_8gpu.err; echo "c3 sample 8 gpu rc=$?"
 kill $SMI
-python -c "
-import json; d=json.load(open('gpurun_out/c3_sample_8gpu.json')); print(d['value'], d['ms_per_step'], d['e2e']['value'] if d['e2e'] else None, [ (r['genes'], round(r['bs_ms_per_step']), round(r['wait_ms_per_step'])) for r in d['ranks']])"
