@@ -52,6 +52,9 @@ typedef enum dn_exit {
     DN_EXIT_FALLBACK_HIGH = 6,  /* nmf.py:342-346  refined DI > 0.9, first fit restored        */
     DN_EXIT_FALLBACK = 7        /* nmf.py:349-353  no baseline, first fit restored             */
 } dn_exit;
+/* A NEGATIVE value in DN_CNT_EXIT (-1) is not a branch of the algorithm: the gene did not fit the plan of the launch it
+ * was put in (its share of candidate columns exceeds plan.ws_cols -- a planner or ABI misuse).  Its outputs then hold
+ * the default result (DI 0, flag 0); callers must treat it as an error (the Python class raises DegnormCudaError). */
 
 /* per-gene int32 counters written by dn_baseline_selection (row = gene id, DN_NCOUNTERS columns) */
 typedef enum dn_counter {
