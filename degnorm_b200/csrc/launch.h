@@ -175,7 +175,7 @@ __host__ __device__ inline int wide_slots(int nb) {
     return s;
 }
 __host__ __device__ inline int wide_kslices(int nb) {
-    int ks = WIDE_THREADS / wide_slots(nb);
+    int ks = (WIDE_THREADS - 32) / wide_slots(nb);     // (one warp is kept free of tiles: it runs the update, nmfoa_wide.cu)
     return ks < 1 ? 1 : (ks > WIDE_MAX_KS ? WIDE_MAX_KS : ks);
 }
 struct WideCarve { long long small, red, binm, alive, ibuf, lw, mbar, part, ring, total; };

@@ -96,7 +96,7 @@ struct WPass {
     unsigned long long *mbar;
     long long slot_stride;
     double c;
-    int n_cur, pp, cs_col, ti, tj, ks, nks, crank, csize, xpar, ne, primed, tile;
+    int n_cur, pp, cs_col, ti, tj, ks, nks, crank, csize, xpar, ne, primed, tile, ovl;
     unsigned seq;
 };
 struct WPassOut { unsigned seq; int xpar; };
@@ -114,8 +114,9 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[r][q] = 0.0;
 
+    const int itid = g.ovl ? (WNW - 1) * 32 : 0;            // the thread that talks to the TMA unit
     auto issue = [&](int ch, bool with_x) {
-        if (tid == 0 && ch < nchunk) {
+        if (tid == itid && ch < nchunk) {
             const unsigned st = (seq0 + (unsigned)ch) % WIDE_RING;
             double *dst = g.ring + st * STG;
             fence_proxy_async_smem();
@@ -133,64 +134,38 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
               ao3 = 8 * g.ti + rot8(6, g.ti);
     const int uo0 = 8 * g.tj + rot8(0, g.tj), uo1 = 8 * g.tj + rot8(2, g.tj), uo2 = 8 * g.tj + rot8(4, g.tj),
               uo3 = 8 * g.tj + rot8(6, g.tj);
-    const int half = tid / WLPC, hl = tid % WLPC;           // phase A: column of the chunk / lane within the column
+    // phase A for one column of a chunk: 16 lanes (hl = 0 .. 15) share it, rows hl, hl + 16, ...
+    auto phase_a = [&](double *sM, int ncol, int col, int hl) {
+        const bool act = col < ncol;
+        double *mc = sM + col * CS;
+        const double *xc = sM + WCH * CS + col * CS;
+        double tp = 0.0;
+        if (act) {
+            double t0 = 0.0, t1 = 0.0;                      // (two chains, four rows in flight)
+            int r = hl;
 #pragma unroll 1
-    for (int ch = 0; ch < nchunk; ++ch) {
-        const unsigned k = seq0 + (unsigned)ch, st = k % WIDE_RING;
-        double *sM = g.ring + st * STG;
-        const int ncol = min(WCH, n - ch * WCH);
-        __syncthreads();                                   // everyone is done with chunk ch - 1
-        if constexpr (UPDATE) {
-            // stage of chunk ch - 1 holds that chunk's final M -> one bulk store; the store of chunk ch - 2 has read
-            // its stage by now -> that stage takes chunk ch + 1
-            if (tid == 0) {
-                if (ch >= 1) {
-                    const unsigned sp = (k - 1) % WIDE_RING;
-                    const int ncp = min(WCH, n - (ch - 1) * WCH);
-                    bulk_s2g(g.M + (long long)(ch - 1) * (WCH * CS), g.ring + sp * STG, (unsigned)(ncp * CS * 8));
-                }
-                bulk_wait_read<1>();
+            for (; r + 3 * WLPC < g.pp; r += 4 * WLPC) {
+                const double m0 = mc[r], m1 = mc[r + WLPC], m2 = mc[r + 2 * WLPC], m3 = mc[r + 3 * WLPC];
+                const double v0 = g.v[r], v1 = g.v[r + WLPC], v2 = g.v[r + 2 * WLPC], v3 = g.v[r + 3 * WLPC];
+                t0 = fma(v0, m0, t0); t1 = fma(v1, m1, t1); t0 = fma(v2, m2, t0); t1 = fma(v3, m3, t1);
             }
-            if (ch + 1 >= 2) issue(ch + 1, true);
-        } else {
-            issue(ch + 2, false);
+            for (; r < g.pp; r += WLPC) t0 = fma(g.v[r], mc[r], t0);
+            tp = t0 + t1;
         }
-        mbar_wait(g.mbar + st, (k / WIDE_RING) & 1u);       // chunk ch has landed
-        if constexpr (UPDATE) {
-            // phase A: 16 lanes per column, rows hl, hl + 16, ...  (columns 0 .. 15 of the chunk: threads 0 .. 255)
-            if (half < WCH) {
-                const bool act = half < ncol;
-                double *mc = sM + half * CS;
-                const double *xc = sM + WCH * CS + half * CS;
-                double tp = 0.0;
-                if (act) {
-                    double t0 = 0.0, t1 = 0.0;                      // (two chains, four rows in flight)
-                    int r = hl;
-#pragma unroll 1
-                    for (; r + 3 * WLPC < g.pp; r += 4 * WLPC) {
-                        const double m0 = mc[r], m1 = mc[r + WLPC], m2 = mc[r + 2 * WLPC], m3 = mc[r + 3 * WLPC];
-                        const double v0 = g.v[r], v1 = g.v[r + WLPC], v2 = g.v[r + 2 * WLPC], v3 = g.v[r + 3 * WLPC];
-                        t0 = fma(v0, m0, t0); t1 = fma(v1, m1, t1); t0 = fma(v2, m2, t0); t1 = fma(v3, m3, t1);
-                    }
-                    for (; r < g.pp; r += WLPC) t0 = fma(g.v[r], mc[r], t0);
-                    tp = t0 + t1;
-                }
 #pragma unroll
-                for (int o = 1; o < WLPC; o <<= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
-                if (act) {
+        for (int o = 1; o < WLPC; o <<= 1) tp += __shfl_xor_sync(0xffffffffu, tp, o);
+        if (act) {
 #pragma unroll 4
-                    for (int r = hl; r < g.pp; r += WLPC) {
-                        const double x = xc[r], m = mc[r];
-                        const double res = fma(g.v[r], tp, -x);
-                        const double w = fma(-g.c, res, m - x);
-                        mc[r] = fma(0.5, w + fabs(w), x);
-                    }
-                }
-                fence_proxy_async_smem();                  // the stage is read by the bulk store later
+            for (int r = hl; r < g.pp; r += WLPC) {
+                const double x = xc[r], m = mc[r];
+                const double res = fma(g.v[r], tp, -x);
+                const double w = fma(-g.c, res, m - x);
+                mc[r] = fma(0.5, w + fabs(w), x);
             }
-            __syncthreads();                               // every thread reads every column in phase B
         }
-        // phase B: this thread's tile over the chunk's columns (its k-slice of them)
+    };
+    // phase B: this thread's tile over the chunk's columns (its k-slice of them)
+    auto phase_b = [&](const double *sM, int ncol) {
         if (has_tile) {
             const double *mc = sM + g.ks * CS;
             const int mstep = g.nks * CS;
@@ -223,13 +198,88 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
                 }
             }
         }
+    };
+    if (g.ovl) {
+        // ---- overlapped schedule (the twelfth warp owns no tile): it runs the TMA traffic and the multiplier update
+        // of chunk ch + 1 WHILE the eleven Gram warps accumulate chunk ch -- one block barrier per chunk instead of
+        // two, and phase A off the critical path.
+        const bool updw = (tid >> 5) == WNW - 1;
+        if (UPDATE && updw && nchunk > 0) {
+            const unsigned k0 = seq0, st0 = k0 % WIDE_RING;
+            mbar_wait(g.mbar + st0, (k0 / WIDE_RING) & 1u);
+            for (int rd = 0; rd < WCH / 2; ++rd) phase_a(g.ring + st0 * STG, min(WCH, n), 2 * rd + (lane >> 4), lane & 15);
+            fence_proxy_async_smem();
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const unsigned k = seq0 + (unsigned)ch, st = k % WIDE_RING;
+            __syncthreads();                               // chunk ch - 1 accumulated everywhere, chunk ch updated
+            if (updw) {
+                if (lane == 0) {
+                    if constexpr (UPDATE) {
+                        if (ch >= 1) {
+                            const unsigned sp = (k - 1) % WIDE_RING;
+                            const int ncp = min(WCH, n - (ch - 1) * WCH);
+                            bulk_s2g(g.M + (long long)(ch - 1) * (WCH * CS), g.ring + sp * STG, (unsigned)(ncp * CS * 8));
+                        }
+                        bulk_wait_read<0>();               // (this warp has a chunk's time to spare)
+                    }
+                    issue(ch + 2, UPDATE);                 // into the stage chunk ch - 1 has just left
+                }
+                __syncwarp();
+                if (UPDATE && ch + 1 < nchunk) {
+                    const unsigned k1 = k + 1, st1 = k1 % WIDE_RING;
+                    mbar_wait(g.mbar + st1, (k1 / WIDE_RING) & 1u);
+                    const int ncol1 = min(WCH, n - (ch + 1) * WCH);
+                    for (int rd = 0; rd < WCH / 2; ++rd) phase_a(g.ring + st1 * STG, ncol1, 2 * rd + (lane >> 4), lane & 15);
+                    fence_proxy_async_smem();              // the stage is read by the bulk store later
+                }
+            } else {
+                if constexpr (!UPDATE) mbar_wait(g.mbar + st, (k / WIDE_RING) & 1u);
+                phase_b(g.ring + st * STG, min(WCH, n - ch * WCH));
+            }
+        }
+    } else {
+    const int half = tid / WLPC, hl = tid % WLPC;           // phase A: column of the chunk / lane within the column
+#pragma unroll 1
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const unsigned k = seq0 + (unsigned)ch, st = k % WIDE_RING;
+        double *sM = g.ring + st * STG;
+        const int ncol = min(WCH, n - ch * WCH);
+        __syncthreads();                                   // everyone is done with chunk ch - 1
+        if constexpr (UPDATE) {
+            // stage of chunk ch - 1 holds that chunk's final M -> one bulk store; the store of chunk ch - 2 has read
+            // its stage by now -> that stage takes chunk ch + 1
+            if (tid == itid) {
+                if (ch >= 1) {
+                    const unsigned sp = (k - 1) % WIDE_RING;
+                    const int ncp = min(WCH, n - (ch - 1) * WCH);
+                    bulk_s2g(g.M + (long long)(ch - 1) * (WCH * CS), g.ring + sp * STG, (unsigned)(ncp * CS * 8));
+                }
+                bulk_wait_read<1>();
+            }
+            if (ch + 1 >= 2) issue(ch + 1, true);
+        } else {
+            issue(ch + 2, false);
+        }
+        mbar_wait(g.mbar + st, (k / WIDE_RING) & 1u);       // chunk ch has landed
+        if constexpr (UPDATE) {
+            // phase A: 16 lanes per column (columns 0 .. 15 of the chunk: threads 0 .. 255)
+            if (half < WCH) {
+                phase_a(sM, ncol, half, hl);
+                fence_proxy_async_smem();                  // the stage is read by the bulk store later
+            }
+            __syncthreads();                               // every thread reads every column in phase B
+        }
+        phase_b(sM, ncol);
+    }
     }
     WPassOut out;
     out.seq = (seq0 + (unsigned)nchunk) % (2 * WIDE_RING);    // (stage, parity) of chunk k depend on k mod 2 RING only
     fence_proxy_async();
     __syncthreads();
     if constexpr (UPDATE) {
-        if (tid == 0 && nchunk > 0) {
+        if (tid == itid && nchunk > 0) {
             const unsigned sp = (seq0 + (unsigned)nchunk - 1u) % WIDE_RING;
             const int ncp = n - (nchunk - 1) * WCH;
             bulk_s2g(g.M + (long long)(nchunk - 1) * (WCH * CS), g.ring + sp * STG, (unsigned)(ncp * CS * 8));
@@ -237,7 +287,7 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
         }
         __syncthreads();
     }
-    if (prime_next && tid == 0) {
+    if (prime_next && tid == itid) {
         for (int q = 0; q < 2 && q < nchunk; ++q) {
             const unsigned st = (out.seq + (unsigned)q) % WIDE_RING;
             double *dst = g.ring + st * STG;
@@ -548,6 +598,7 @@ __device__ void run_nmf_wide(const KArgs &a, WGene &g, const WTile &t, bool firs
     pa.slot_stride = g.slot_stride; pa.c = a.c; pa.n_cur = g.n_cur; pa.pp = g.pp; pa.cs_col = g.cs_col;
     pa.ti = t.ti; pa.tj = t.tj; pa.ks = t.ks; pa.nks = g.ks; pa.crank = g.crank; pa.csize = g.csize; pa.ne = g.ne;
     pa.tile = t.tile;
+    pa.ovl = (wide_slots(g.nb) * g.ks <= (WNW - 1) * 32) ? 1 : 0;       // the twelfth warp owns no tile
     double acc[8][8];
     for (int it = -1; it < T; ++it) {
         pa.seq = g.seq;
