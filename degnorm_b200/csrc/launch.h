@@ -166,6 +166,9 @@ constexpr int WIDE_MAX_PP = 208;      // 26 x 27 / 2 = 351 tiles <= threads: the
 constexpr int WIDE_MIN_P = 49;
 constexpr int WIDE_MAX_KS = 8;        // k-slices of a chunk's columns when there are fewer tiles than threads
 constexpr int WIDE_NSMALL = 11;       // pp-sized shared vectors
+#ifndef WIDE_OVERLAP                  // 1: the twelfth warp runs the update of chunk ch + 1 while the others accumulate chunk ch
+#define WIDE_OVERLAP 0                //    (one block barrier per chunk) -- measured SLOWER: one warp cannot update 16 columns of
+#endif                                //    200 rows in the time eleven warps need for their tiles (C5 sample 13.0 -> 7.7 genes/s)
 __host__ __device__ inline int wide_pp(int p) { return (p + 7) / 8 * 8; }
 __host__ __device__ inline int wide_tiles(int pp) { return (pp / 8) * (pp / 8 + 1) / 2; }
 // lane slots of one k-slice: the tiles row-major, every tile row padded to an even length (nmfoa_wide.cu)
@@ -175,7 +178,7 @@ __host__ __device__ inline int wide_slots(int nb) {
     return s;
 }
 __host__ __device__ inline int wide_kslices(int nb) {
-    int ks = (WIDE_THREADS - 32) / wide_slots(nb);     // (one warp is kept free of tiles: it runs the update, nmfoa_wide.cu)
+    int ks = (WIDE_THREADS - (WIDE_OVERLAP ? 32 : 0)) / wide_slots(nb);   // (overlapped schedule: one warp kept free of tiles)
     return ks < 1 ? 1 : (ks > WIDE_MAX_KS ? WIDE_MAX_KS : ks);
 }
 struct WideCarve { long long small, red, binm, alive, ibuf, lw, mbar, part, ring, total; };

@@ -199,10 +199,10 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
             }
         }
     };
-    if (g.ovl) {
-        // ---- overlapped schedule (the twelfth warp owns no tile): it runs the TMA traffic and the multiplier update
-        // of chunk ch + 1 WHILE the eleven Gram warps accumulate chunk ch -- one block barrier per chunk instead of
-        // two, and phase A off the critical path.
+    if (WIDE_OVERLAP && g.ovl) {
+        // ---- overlapped schedule (WIDE_OVERLAP = 1; the twelfth warp owns no tile): it runs the TMA traffic and the
+        // multiplier update of chunk ch + 1 WHILE the eleven Gram warps accumulate chunk ch -- one block barrier per
+        // chunk instead of two.  Parity-tested, measured slower (see launch.h) and off by default.
         const bool updw = (tid >> 5) == WNW - 1;
         if (UPDATE && updw && nchunk > 0) {
             const unsigned k0 = seq0, st0 = k0 % WIDE_RING;
@@ -598,7 +598,7 @@ __device__ void run_nmf_wide(const KArgs &a, WGene &g, const WTile &t, bool firs
     pa.slot_stride = g.slot_stride; pa.c = a.c; pa.n_cur = g.n_cur; pa.pp = g.pp; pa.cs_col = g.cs_col;
     pa.ti = t.ti; pa.tj = t.tj; pa.ks = t.ks; pa.nks = g.ks; pa.crank = g.crank; pa.csize = g.csize; pa.ne = g.ne;
     pa.tile = t.tile;
-    pa.ovl = (wide_slots(g.nb) * g.ks <= (WNW - 1) * 32) ? 1 : 0;       // the twelfth warp owns no tile
+    pa.ovl = (WIDE_OVERLAP && wide_slots(g.nb) * g.ks <= (WNW - 1) * 32) ? 1 : 0;       // the twelfth warp owns no tile
     double acc[8][8];
     for (int it = -1; it < T; ++it) {
         pa.seq = g.seq;
