@@ -162,54 +162,84 @@ __device__ __forceinline__ FinArgs fin_args(const MGene &g) {
 // (returns the exchange-slot parity to use next)
 __device__ __forceinline__ int gram_finish(FinArgs g, double (&acc)[8][6]) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- the 8 warps' partials -> CTA sum (fixed halving tree through shared memory)
+    // ---- the warps' partials -> CTA sum, in the order of a fixed halving tree: ((w0 + w4) + (w2 + w6)) + ((w1 + w5) +
+    // (w3 + w7)).  Eight warps: the upper four park their tiles in four shared slots, the lower four add them and write
+    // their sums back to the same slots (two block barriers); the last two levels of the tree are folded into the
+    // reader below, which adds the four slots in tree order (the full tree took eight barriers per pass).
     const int tile = g.tab[4 * lane + 2];                       // dense tile id of this lane's slot (-1: pad slot)
-    double *mine = g.buf + (long long)(warp & 3) * MNE + (tile >= 0 ? tile : 0) * 48;
-    for (int half = MNW / 2; half >= 1; half >>= 1) {
-        if (warp >= half && warp < 2 * half && tile >= 0) {
-            double *dst = g.buf + (long long)(warp - half) * MNE + tile * 48;
+    constexpr int NSLOT = MNW == 8 ? 4 : 1;
+    if constexpr (MNW == 8) {
+        double *slot_ = g.buf + (long long)(warp & 3) * MNE + (tile >= 0 ? tile : 0) * 48;
+        if (warp >= 4 && warp < 8 && tile >= 0) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int q = 0; q < 6; q += 2)
-                    *reinterpret_cast<double2 *>(dst + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+                    *reinterpret_cast<double2 *>(slot_ + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
         }
         __syncthreads();
-        if (warp < half && tile >= 0) {
+        if (warp < 4 && tile >= 0) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int q = 0; q < 6; q += 2) {
-                    const double2 t = *reinterpret_cast<const double2 *>(mine + r * 6 + q);
-                    acc[r][q] += t.x;
-                    acc[r][q + 1] += t.y;
+                    const double2 t = *reinterpret_cast<const double2 *>(slot_ + r * 6 + q);
+                    *reinterpret_cast<double2 *>(slot_ + r * 6 + q) = make_double2(acc[r][q] + t.x, acc[r][q + 1] + t.y);
                 }
         }
         __syncthreads();
-    }
-    if (warp == 0 && tile >= 0) {
+    } else {
+        double *mine = g.buf + (long long)(warp & 3) * MNE + (tile >= 0 ? tile : 0) * 48;
+        for (int half = MNW / 2; half >= 1; half >>= 1) {
+            if (warp >= half && warp < 2 * half && tile >= 0) {
+                double *dst = g.buf + (long long)(warp - half) * MNE + tile * 48;
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
+                for (int r = 0; r < 8; ++r)
 #pragma unroll
-            for (int q = 0; q < 6; q += 2)
-                *reinterpret_cast<double2 *>(g.buf + tile * 48 + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+                    for (int q = 0; q < 6; q += 2)
+                        *reinterpret_cast<double2 *>(dst + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+            }
+            __syncthreads();
+            if (warp < half && tile >= 0) {
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+#pragma unroll
+                    for (int q = 0; q < 6; q += 2) {
+                        const double2 t = *reinterpret_cast<const double2 *>(mine + r * 6 + q);
+                        acc[r][q] += t.x;
+                        acc[r][q + 1] += t.y;
+                    }
+            }
+            __syncthreads();
+        }
+        if (warp == 0 && tile >= 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+#pragma unroll
+                for (int q = 0; q < 6; q += 2)
+                    *reinterpret_cast<double2 *>(g.buf + tile * 48 + r * 6 + q) = make_double2(acc[r][q], acc[r][q + 1]);
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    auto cta_sum = [&](int e) -> double {
+        if constexpr (NSLOT == 4) return (g.buf[e] + g.buf[2 * MNE + e]) + (g.buf[MNE + e] + g.buf[3 * MNE + e]);
+        else return g.buf[e];
+    };
     // ---- cluster sum (rank order) and scatter into the square G
-    const double *src = g.buf;
+    bool local = true;
     if (g.csize > 1) {
         cg::cluster_group cl = cg::this_cluster();
         double *slot = g.slots + (long long)g.xpar * MNE;
-        for (int e = tid; e < MNE; e += MNT) slot[e] = g.buf[e];
+        for (int e = tid; e < MNE; e += MNT) slot[e] = cta_sum(e);
         __threadfence();
         cl.sync();
-        src = nullptr;
+        local = false;
     }
     const double *first = g.slots - (long long)g.crank * g.slot_stride + (long long)g.xpar * MNE;
     for (int e = tid; e < MNE; e += MNT) {
         double s;
-        if (src) {
-            s = src[e];
+        if (local) {
+            s = cta_sum(e);
         } else {
             s = 0.0;
             for (int r = 0; r < g.csize; ++r) s += __ldcg(first + (long long)r * g.slot_stride + e);
