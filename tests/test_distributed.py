@@ -148,6 +148,55 @@ def test_gloo_two_workers_equal_one():
         np.testing.assert_allclose(g[5], ref["scale_factors"], rtol=1e-13)
 
 
+def _subgroup_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from degnorm_b200.distributed import TorchComm
+        grp = dist.new_group(ranks=[1, 2])                   # a group that does not start at global rank 0
+        out = None
+        if rank in (1, 2):
+            c = TorchComm(grp)
+            assert (c.rank, c.size) == (rank - 1, 2)
+            if c.rank == 0:
+                c.send_obj({"hello": 42}, dest=1, tag=333)       # group rank 1 = global rank 2
+                got = c.recv_obj(source=1, tag=666)
+            else:
+                got = c.recv_obj(source=0, tag=333)
+                c.send_obj("back", dest=0, tag=666)
+            t = torch.tensor([float(rank)], dtype=torch.float64)
+            c.allreduce_(t)
+            c.barrier()
+            out = (got, float(t.item()))
+        q.put((rank, out))
+    except Exception as exc:
+        import traceback
+        q.put((rank, "ERROR: %s\n%s" % (exc, traceback.format_exc())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_torchcomm_speaks_group_ranks_in_a_subgroup():
+    """TorchComm takes group ranks (as run_gene_nmfoa_mpi does); torch's object send/recv take GLOBAL ranks: in a
+    sub-group that does not start at global rank 0 the two differ."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subgroup_worker, args=(r, 3, port, q)) for r in range(3)]
+    for pr in procs:
+        pr.start()
+    got = dict(q.get(timeout=240) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    assert got[0] is None
+    assert got[1] == ("back", 3.0) and got[2] == ({"hello": 42}, 3.0), got
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 def _gpu_worker(rank, world, port, q, partition):
     import torch.distributed as dist
