@@ -277,6 +277,8 @@ def main():
             vals.append(cb["value"])
         v = float(np.mean(vals))
         cb["value"] = v
+        if cb.get("port_over_reference_speed"):
+            cb["unmodified_reference_estimate"] = v / cb["port_over_reference_speed"]
         cb["sample"] += "; %d steps, each a fresh sample" % len(vals)
         emit(dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                   ms_per_step=1000.0 * n_total / v, higher_is_better=True, scaling="strong" if strong else "weak",
