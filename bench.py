@@ -81,6 +81,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="e2e: only the headline flow")
+    ap.add_argument("--variants", action="store_true",
+                    help="e2e: also time the eager-estimates and zero-copy-input flows (default: only in short runs, steps <= 5)")
     ap.add_argument("--serial-buckets", action="store_true", help="tuning: run the tiers one after another")
     ap.add_argument("--force-cluster", type=int, default=0, help="tuning: every gene through clusters of this size")
     ap.add_argument("--force-streamed", action="store_true", help="tuning: every gene through the streamed tier")
@@ -517,7 +519,8 @@ def main():
                    input="separately allocated p x L matrices (packed into pinned staging inside the timed region)",
                    flow="GeneNMFOA(return_estimates='lazy').run(cov_dict, reads)")
         del model, est
-        if not args.no_variants:
+        if not args.no_variants and (args.variants or args.steps <= 5):
+            # (long runs -- the driver's 25 steps -- keep to the headline flow: every variant costs two more full runs)
             variants = {}
             sec_e, model, est = time_flow(cov_sep, True, reps=1, warm=1)
             variants["eager_estimates"] = dict(value=genes_all_ranks / sec_e, seconds_per_step=sec_e,
