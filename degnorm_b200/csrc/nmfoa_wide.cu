@@ -46,7 +46,7 @@ constexpr int WRPL = (WIDE_MAX_PP + WLPC - 1) / WLPC;   // rows per lane there (
 
 struct WGene {
     double *v, *K, *K0, *rs0, *rsF, *rsC, *rsC0, *rho, *scale, *tmp, *diag, *red, *binm, *part, *ring;
-    int *alive, *ibuf, *lw, *tab;
+    int *alive, *ibuf, *lw;
     double *X, *M, *resb, *tb, *Gfull, *slots, *kslab;      // global (slab)
     long long slot_stride;
     int pp, cs_col, nb, ntiles, ks, ne;
@@ -350,7 +350,6 @@ __device__ __forceinline__ WPassOut gram_wide(const WPass g, const bool prime_ne
         out.xpar = g.xpar ^ 1;
         __syncthreads();
     }
-    (void)lane;
     return out;
 }
 

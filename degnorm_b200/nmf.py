@@ -151,9 +151,10 @@ class GeneNMFOA(object):
 
     def ratio_svd(self, x):
         """nmf.py:109-121: rank-one product clamped from below by x."""
-        _, _, eng, _ = _factorise(x, 0, self.device)
+        eng, x = _single_matrix_engine(x, self.device, degnorm_iter=1, nmf_iter=0, min_high_coverage=2,
+                                       skip_baseline_selection=True)
         out = eng.fit_once(flags=_lib.DN_FLAG_PLAIN_NMF, want_estimates=True, clamp_estimates=True)
-        return out["est"].cpu().numpy().reshape(np.shape(x))
+        return out["est"].cpu().numpy().reshape(x.shape)
 
     def run_ratio_svd_serial(self, x):
         """nmf.py:123-124"""
