@@ -33,3 +33,16 @@ def test_gpu_arm_needs_cuda():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--genes", "8"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_committed_traffic_record_matches_the_default_workload():
+    """roofline.traffic is quoted from the ncu launch list of the headline command (profiles/r02_traffic_c3.json):
+    it only applies while bench.py's default C3 sample is the workload that list was taken on."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_c3.json")))
+    assert rec["config"] == "c3" and rec["genes"] == bench.DEFAULT_GENES["c3"]
+    assert rec["outer_iterations"] == bench.RUN_KW["degnorm_iter"]
+    # DRAM traffic of the fused launches within a few per cent of the algorithmic bytes (nothing re-read)
+    assert 0.9 < rec["dram_bytes_per_launch_group"] / 13.49e12 < 1.05
