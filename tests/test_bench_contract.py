@@ -11,8 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+    import time
+    t0 = time.perf_counter()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0",
                         "--cpu-genes", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    wall = time.perf_counter() - t0
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, r.stdout
@@ -24,6 +27,10 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "model" not in d["config"]
+    # ms_per_step is the wall time a step really took here (the driver holds steps x ms_per_step against its own clock);
+    # the time the whole workload would take at `value` is a separate key
+    assert 0 < d["steps"] * d["ms_per_step"] / 1000.0 <= wall
+    assert d["ms_full_workload"] == pytest.approx(1000.0 * d["config"]["genes"] / d["value"])
 
 
 def test_gpu_arm_needs_cuda():
