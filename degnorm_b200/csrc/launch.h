@@ -111,9 +111,10 @@ __host__ __device__ inline long long small_slab_doubles(int P, long long ws_cols
 }
 
 // ---- mid-p kernel (13 <= p <= 48; nmfoa_mid.cuh): streamed, CTA-level TMA ring of (8 x warps)-column chunks ------
-// Three instantiations: warp-specialised (default: 8 Gram warps + 4 update warps, one CTA per SM, 64-column chunks,
-// no block barrier inside a pass), 8 warps (one CTA per SM, every warp updates and accumulates, one block barrier per
-// chunk) and 4 warps (two such CTAs per SM, 32-column chunks).
+// Three instantiations: 8 warps (default: one CTA per SM, every warp updates and accumulates its own columns, one
+// block barrier per 64-column chunk), 4 warps (two such CTAs per SM, 32-column chunks) and warp-specialised (8 Gram
+// warps + 4 update warps, one CTA per SM, 32-column chunks in a 6-stage ring, no block barrier inside a pass; measured
+// no faster than the 8-warp one: profiles/r02_mid_variants.md).
 constexpr int MID_P = 48;             // samples padded to this
 constexpr int MID_WARPS = 8;          // Gram warps per CTA
 constexpr int MID_UPD_WARPS = 4;      // update warps of the warp-specialised instantiation

@@ -96,7 +96,8 @@ class ShardEngine(object):
         self.use_wide = True
         self.wide_clusters = None
         self.mid_clusters = None
-        self.mid_warps = 0                # 0: 8 warps, one CTA per SM; 4: two 4-warp CTAs per SM
+        self.mid_warps = 0                # 0 / 8: 8 warps, one CTA per SM (default); 4: two 4-warp CTAs per SM;
+                                          # 12: warp-specialised (8 Gram + 4 update warps), measured no faster
         self.force_cluster = 0
         self.clusters = (2, 4, 8, 16)
         self.stream_clusters = ((4, 65536), (8, 262144))       # (cluster size, up to this many candidate columns)
