@@ -39,6 +39,17 @@ namespace {
 // error by lambda_2/lambda_1 (typically 0.05-0.2), so the vector returned is within ~1e-14 of the eigenvector.
 constexpr double SMALL_EIG_TOL = 1.0e-13;
 
+// streamed tier: Gram rounds of one 32-column block whose operand loads are issued back to back (tuning knob; the
+// order of the sums does not depend on it)
+#ifndef SMALL_STREAM_UNROLL
+#define SMALL_STREAM_UNROLL 4
+#endif
+constexpr int STREAM_UNROLL = SMALL_STREAM_UNROLL;
+#ifndef SMALL_RES_UNROLL      // the same for the shared-memory resident tiers
+#define SMALL_RES_UNROLL 4
+#endif
+constexpr int RES_UNROLL = SMALL_RES_UNROLL;
+
 template <int P> struct SmallCfg;
 // TC: tile columns (tile = 2 rows x TC columns of G), NTILE tiles cover the upper triangle, NTP = tiles padded
 // to a power of two, KS = k-slices (lanes = NTP * KS)
@@ -281,7 +292,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
             if (g.tpack >= 0) {
                 const int nb = min(32, c_hi - blk * 32);
                 const double *mc = stage + ks * CS;
-#pragma unroll 4
+#pragma unroll STREAM_UNROLL
                 for (int j = ks; j < nb; j += KS, mc += KS * CS) {
                     const double2 ar = *reinterpret_cast<const double2 *>(mc + oR);
                     const double2 ua = *reinterpret_cast<const double2 *>(mc + oA);
@@ -331,7 +342,7 @@ __device__ __forceinline__ void gram_small(const KArgs &a, SGene &g, const doubl
     if (g.tpack >= 0) {
         // phase B: this lane's Gram tile over its k-slice of the warp's columns
         const double *mc = g.M + (c_lo + ks) * CS;
-#pragma unroll 4
+#pragma unroll RES_UNROLL
         for (int col = c_lo + ks; col < c_hi; col += KS, mc += KS * CS) {
             const double2 ar = *reinterpret_cast<const double2 *>(mc + oR);
             const double2 ua = *reinterpret_cast<const double2 *>(mc + oA);
