@@ -306,8 +306,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    group = None
+    group, numa = None, None
     if world > 1:
+        # one rank per GPU: stay on the GPU's NUMA node (pinned staging buffers are first-touched there), best effort
+        from degnorm_b200.distributed import pin_to_gpu_numa_node
+        numa = pin_to_gpu_numa_node(local)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
 
@@ -551,7 +554,7 @@ def main():
                   ms_per_step=ms_per_step, higher_is_better=True, scaling="strong" if strong else "weak",
                   vs_baseline=None, dtype="f64", data="synthetic", config=config, e2e=e2e, gpu_launches=launches,
                   roofline=roofline, cpu_baseline=cb, clocks=clock_summary, fp64_peak=fp64, ranks=ranks,
-                  algorithmic_bytes_per_step=total_bytes, algorithmic_parts=parts))
+                  algorithmic_bytes_per_step=total_bytes, algorithmic_parts=parts, numa=numa))
     if world > 1:
         dist.destroy_process_group()
 

@@ -43,6 +43,46 @@ def balanced_partition(cost, size):
     return [np.flatnonzero(owner == w) for w in range(size)]
 
 
+def parse_cpulist(text):
+    """'0-3,8,10-11' (the format of /sys/devices/system/node/nodeN/cpulist) -> sorted list of CPU numbers."""
+    cpus = set()
+    for part in text.strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return sorted(cpus)
+
+
+def pin_to_gpu_numa_node(device_index, min_cpus=4, sysfs="/sys"):
+    """One process per GPU: keep this process (and the pinned staging memory it will first-touch) on the NUMA node
+    the GPU hangs off, so that eight ranks packing and uploading at once do not cross the socket interconnect.
+    Best effort: returns a dict saying what was done; leaves the affinity alone when the node is unknown (-1), the
+    sysfs files are missing, or fewer than `min_cpus` of the node's CPUs are in this process's current affinity."""
+    import os
+    import torch
+    info = dict(pinned=False)
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        info["pci"] = bdf
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")).read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpus = parse_cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read())
+        mine = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        info["cpus"] = len(mine)
+        if len(mine) < min_cpus:
+            return info
+        os.sched_setaffinity(0, mine)
+        info["pinned"] = True
+    except Exception as e:          # (no sysfs, no such device, not permitted ...)
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 class SoloComm(object):
     rank, size = 0, 1
 

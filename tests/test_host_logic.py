@@ -331,3 +331,15 @@ def test_mid_kernel_plans_are_pure_host_arithmetic():
     assert plan(40000, 1000, 0, 16).ctas == 144                                   # 9 clusters of 16 on 148 SMs
     pl = _lib.DnPlan()
     assert lib.dn_make_plan(C.byref(prm), 5000, 10, 0, 0, 0, 3, sm, smem, C.byref(pl)) != 0      # cluster of 3
+
+
+def test_numa_pinning_helper_is_best_effort(tmp_path):
+    """distributed.pin_to_gpu_numa_node: cpulist parsing, and no exception (nor any change of affinity) when the
+    device or the sysfs files are not there."""
+    import os
+    from degnorm_b200.distributed import parse_cpulist, pin_to_gpu_numa_node
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("5") == [5] and parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    info = pin_to_gpu_numa_node(0, sysfs=str(tmp_path))
+    assert info["pinned"] is False and os.sched_getaffinity(0) == before
